@@ -1,0 +1,100 @@
+/*
+ * pregraph_b200.h -- C-ABI of libpregraph_b200.so, the B200-native replacement for SOAPdenovo2's `pregraph` stage.
+ *
+ * Plain C: pointers, sizes, ints.  No CUDA / torch / C++ types cross this boundary; errors never unwind across it
+ * (every int-returning entry point returns 0 on success, non-zero on failure, message via pgb200_last_error()).
+ *
+ * What each entry point replaces in the reference (file:line relative to /root/reference/standardPregraph/):
+ *
+ *   call_pregraph                 int call_pregraph(int argc, char **argv)            pregraph.c:62  (declared main.c:29,
+ *                                 called main.c:74 and main.c:341).  Same argv contract ("pregraph -s cfg -o prefix
+ *                                 [-K k -p P -a G -d D -R]"), same files written, same stderr counters, returns 0.
+ *   pgb200_pregraph_main          the same with the 63-mer / 127-mer build flavour chosen at run time (the reference
+ *                                 compiles two binaries with -DMER63 / -DMER127, Makefile:51-66).
+ *   pgb200_feed_text + pgb200_finish_pass1 + pgb200_sweeps
+ *                                 boolean prlRead2HashTable(char *libfile, char *outfile)   prlHashReads.c:304
+ *                                 (readers readseq1by1.c:138-360, chopKmer4read :163-259, put_kmerset newhash.c:473-528,
+ *                                  thread_delow/thread_mark/freqStat :953-1132)
+ *   pgb200_build_layout           the iteration order implied by KmerSets[] (newhash.c:200-233, 473-528)
+ *   pgb200_remove_tips            void removeSingleTips(), void removeMinorTips()     cutTipPreGraph.c:363, 414
+ *   pgb200_kmer2edges             void kmer2edges(char *outfile)                      node2edge.c:61
+ *   pgb200_read2edge              void prlRead2edge(char *libfile, char *outfile)     prlRead2path.c:786
+ *   pgb200_output_vertex          void output_vertex(char *outfile)                   output_pregraph.c:50
+ *   pgb200_destroy                void free_Sets(KmerSet **, int)                     newhash.c:601
+ *
+ * Threading: call from one host thread per engine; an engine owns one GPU stream; everything has completed on the
+ * device when a call returns.  Not re-entrant per engine (the reference is not re-entrant at all).
+ */
+#ifndef PREGRAPH_B200_H
+#define PREGRAPH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pgb200_engine pgb200_engine;
+
+typedef struct pgb200_params {
+    int K;            /* k-mer size after the reference's fix-ups (odd, 13..63 or 13..127)                     */
+    int P;            /* -p: number of reference hash sets; a LAYOUT parameter, not a thread count              */
+    int initG;        /* -a: reference memory assumption in GB (static tables); 0 = dynamic                     */
+    int D;            /* -d: k-mers with frequency <= D are deleted                                             */
+    int repsTie;      /* -R                                                                                      */
+    int flavour127;   /* 0 = SOAPdenovo-63mer semantics, 1 = SOAPdenovo-127mer semantics                        */
+    int device;       /* CUDA device ordinal                                                                     */
+    int max_rd_len;   /* maxReadLen4all (config max_rd_len, default 100)                                         */
+    uint64_t table_slots; /* GPU k-mer table capacity hint (0 = derive from -a / grow on demand)                */
+    int verbose;
+    int world, rank;  /* k-mer space sharding across GPUs: this engine keeps keys whose owner hash % world == rank */
+} pgb200_params;
+
+typedef struct pgb200_pass1_stats {
+    uint64_t records, reads_kept, instances, distinct, table_slots, launches;
+    double ms_decode, ms_insert;
+} pgb200_pass1_stats;
+
+const char *pgb200_last_error(void);
+void pgb200_default_params(pgb200_params *p);
+pgb200_engine *pgb200_create(const pgb200_params *p);
+void pgb200_destroy(pgb200_engine *e);
+
+/* pinned host staging buffers for pgb200_feed_text(on_device = 0) */
+void *pgb200_host_alloc(size_t bytes);
+void pgb200_host_free(void *p);
+
+/* Pass 1.  `text` holds whole FASTA (single-line) or FASTQ (4-line) records, starts at a record start, ends with '\n'.
+ * on_device != 0: `text` is a device pointer (16-byte aligned).  Record i gets stream ordinal ord_base + i*ord_stride
+ * (stride 2 + mate offset for f1/f2, q1/q2 files: the reference interleaves mates, prlHashReads.c:480-583).       */
+int pgb200_feed_text(pgb200_engine *e, const char *text, size_t nbytes, int on_device, int fastq, uint64_t ord_base,
+                     uint64_t ord_stride, int reverse_seq, int maxlen);
+uint64_t pgb200_last_chunk_records(pgb200_engine *e);
+int pgb200_finish_pass1(pgb200_engine *e, pgb200_pass1_stats *st);
+int pgb200_reset_pass1(pgb200_engine *e);
+/* delow (-d) + mark linear + coverage histogram: hist[c] = number of k-mers with coverage c (the .kmerFreq lines are hist[1..255]) */
+int pgb200_sweeps(pgb200_engine *e, long long hist[256], uint64_t *linear_marked, uint64_t *removed);
+
+int pgb200_build_layout(pgb200_engine *e);
+uint64_t pgb200_node_count(pgb200_engine *e);
+/* parity/debug: node_count() records {kmer words (2 or 4 x u64), l[4], r[4], cov, flags(1 single, 2 linear, 4 deleted)}
+ * in reference iteration order; record size = 8*words + 10 bytes                                                    */
+int pgb200_dump_nodes(pgb200_engine *e, void *out);
+
+typedef struct pgb200_graph_stats {
+    uint64_t single_tips, minor_tips, num_ed, edges, extra_nodes, deleted_reads, arcs, vertices;
+} pgb200_graph_stats;
+int pgb200_remove_tips(pgb200_engine *e, pgb200_graph_stats *st);
+int pgb200_kmer2edges(pgb200_engine *e, const char *outfile_prefix, pgb200_graph_stats *st);
+int pgb200_read2edge(pgb200_engine *e, const char *outfile_prefix, pgb200_graph_stats *st);
+int pgb200_output_vertex(pgb200_engine *e, const char *outfile_prefix, pgb200_graph_stats *st);
+
+/* The drop-in stage entry points. */
+int pgb200_pregraph_main(int argc, char **argv, int flavour127);
+int call_pregraph(int argc, char **argv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,138 @@
+// engine_impl.cuh -- EngineT<NW>: device state + phase methods; the methods are defined across decode.cu, pass1.cu,
+// layout.cu, tips.cu, edges.cu, pass2.cu and explicitly instantiated for NW = 2 (K <= 63) and NW = 4 (K <= 127).
+#pragma once
+#include "engine.h"
+#include "kmer.cuh"
+#include "table.cuh"
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace pgb {
+
+#define PG_CUDA(call)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess) {                                                                             \
+            char b__[512];                                                                                    \
+            snprintf(b__, sizeof b__, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__, \
+                     cudaGetErrorString(e__));                                                                \
+            throw std::runtime_error(b__);                                                                    \
+        }                                                                                                     \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void alloc(size_t n) {
+        release();
+        if (n == 0) n = 16;
+        PG_CUDA(cudaMalloc(&p, n));
+        bytes = n;
+    }
+    void ensure(size_t n) { if (n > bytes) alloc(n + n / 4); }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// One fed text chunk, decoded: 2-bit packed reads (LSB-first, W64 words per read) + lengths.  Stays resident in HBM so
+// that pass 2 re-scans the reads without touching the text again (the reference re-parses every file, prlRead2path.c:786).
+struct ReadChunk {
+    u64* words = nullptr;
+    u32* len = nullptr;
+    u64 n_rec = 0;
+    u64 ord_base = 0, ord_stride = 1;
+};
+
+enum Counter { C_DISTINCT = 0, C_INSTANCES, C_KEPT, C_LINEAR, C_REMOVED, C_MISC0, C_MISC1, C_MISC2, C_COUNT = 16 };
+
+template <int NW>
+class EngineT : public IEngine {
+public:
+    explicit EngineT(const PgParams& p);
+    ~EngineT() override;
+
+    void feed_text(const char* text, size_t nbytes, bool on_device, int fastq, uint64_t ord_base, uint64_t ord_stride,
+                   int reverse_seq, int maxlen) override;
+    uint64_t last_chunk_records() const override { return last_records_; }
+    void finish_pass1(Pass1Stats* st) override;
+    void reset_pass1() override;
+    void sweeps(SweepStats* st) override;
+    void build_layout() override;
+    uint64_t node_count() const override { return n_nodes_; }
+    void dump_nodes(void* host_out) override;
+    void remove_tips(TipStats* st) override;
+    void build_edges(EdgeStats* st, std::string* edge_text) override;
+    void pass2(Pass2Stats* st, std::string* prearc_text, std::string* path_bin, std::string* mark_text) override;
+    void vertices(std::string* vertex_text, uint64_t* n_vertex) override;
+
+    // ---- state
+    PgParams prm_;
+    KParams<NW> kp_;
+    cudaStream_t st_ = nullptr;
+    cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+    int W64_ = 0;   // packed words per read
+
+    std::vector<ReadChunk> chunks_;
+    uint64_t last_records_ = 0, total_records_ = 0;
+    Pass1Stats p1_;
+
+    Table<NW> tab_{nullptr, 0};
+    u64 cap_ = 0;
+    DevBuf tab_buf_;
+    u64* d_cnt_ = nullptr;      // Counter[]
+    u64* h_cnt_ = nullptr;      // pinned mirror
+
+    // decode scratch
+    DevBuf text_buf_, line_buf_, scan_buf_;
+
+    // layout: reference geometry
+    u64 set_size_ = 0;          // prime size of every reference set (static -a mode)
+    u64 n_nodes_ = 0;           // distinct k-mers == entries in iteration order
+    DevBuf order_buf_;          // u64 order[n_nodes_] : iteration index -> ktab slot
+    bool layout_exact_ = false;
+
+    // edges / pass 2 state
+    u64 num_ed_ = 0;
+    DevBuf patch_buf_;          // (K+1)-mer patch table
+    u64 patch_mask_ = 0;
+
+    // helpers
+    void ensure_table(u64 need_free);
+    void grow_table(u64 new_cap);
+    void alloc_table(u64 cap);
+    void sync() { PG_CUDA(cudaStreamSynchronize(st_)); }
+    void read_counters() {
+        PG_CUDA(cudaMemcpyAsync(h_cnt_, d_cnt_, C_COUNT * sizeof(u64), cudaMemcpyDeviceToHost, st_));
+        sync();
+    }
+};
+
+// reference table geometry helpers (newhash.c:142-185, 200-233; prlHashReads.c:369-390)
+inline bool ref_is_prime(u64 n) {
+    if (n < 4) return true;
+    if (n % 2 == 0) return false;
+    u64 mx = (u64)__builtin_sqrtf((float)n);   // float sqrt, strict '<': squares of primes count as prime
+    for (u64 i = 3; i < mx; i += 2)
+        if (n % i == 0) return false;
+    return true;
+}
+inline u64 ref_next_prime(u64 n) {
+    if (n % 2 == 0) n++;
+    while (!ref_is_prime(n)) n += 2;
+    return n;
+}
+inline u64 ref_static_set_size(int initG, int P, bool flavour127) {
+    u64 want = (u64)((double)initG * 1024.0f * 1024.0f * 1024.0f / (double)P / (flavour127 ? 40 : 24)), k = 0;
+    do ++k; while (k * 0xFFFFFFULL < want);
+    u64 init = k * 0xFFFFFFULL;
+    return init < 3 ? 3 : ref_next_prime(init);
+}
+
+}   // namespace pgb

@@ -1,0 +1,444 @@
+// host.cpp -- host orchestration behind the unchanged `pregraph -s cfg -K k -p P [-a G] [-d D] [-R] -o prefix` CLI,
+// plus the extern "C" veneer declared in include/pregraph_b200.h.
+//
+// Mirrors, in new code, the host-side behaviour of (standardPregraph/):
+//   call_pregraph / initenv        pregraph.c:62-220   (getopt string, K fix-ups, phase order, stderr lines)
+//   scan_libInfo / splitColumn     lib.c:70-506        (key=value config, [LIB] sections, sort by avg_ins)
+//   openNextFile / nextValidIndex  prlHashReads.c:903-951, readseq1by1.c:595-674 (library + file-type iteration order)
+//   file writers                   prlHashReads.c:1104-1132 (.kmerFreq), node2edge.c:61-70 (.edge.gz via zlib),
+//                                  prlRead2path.c:426-476 (.preArc/.markOnEdge), output_pregraph.c:50-86 (.vertex, .preGraphBasic)
+// All k-mer work happens on the GPU through IEngine; this file only moves bytes between files and the engine.
+#include "../../include/pregraph_b200.h"
+#include "engine.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <getopt.h>
+#include <unistd.h>
+#include <zlib.h>
+#include <cuda_runtime_api.h>
+
+using namespace pgb;
+
+static thread_local std::string g_err;
+struct pgb200_engine {
+    IEngine* e;
+    PgParams prm;
+};
+
+#define PG_TRY try {
+#define PG_CATCH                                   \
+    }                                              \
+    catch (const std::exception& ex) {             \
+        g_err = ex.what();                         \
+        return -1;                                 \
+    }                                              \
+    catch (...) {                                  \
+        g_err = "unknown error";                   \
+        return -1;                                 \
+    }                                              \
+    return 0;
+
+extern "C" const char* pgb200_last_error(void) { return g_err.c_str(); }
+
+extern "C" void pgb200_default_params(pgb200_params* p) {
+    memset(p, 0, sizeof *p);
+    p->K = 23; p->P = 8; p->max_rd_len = 100; p->world = 1;
+}
+
+extern "C" pgb200_engine* pgb200_create(const pgb200_params* p) {
+    try {
+        PgParams q;
+        q.K = p->K; q.P = p->P; q.initG = p->initG; q.D = p->D; q.repsTie = p->repsTie; q.flavour127 = p->flavour127;
+        q.device = p->device; q.max_rd_len = p->max_rd_len > 0 ? p->max_rd_len : 100; q.table_slots = p->table_slots;
+        q.verbose = p->verbose; q.world = p->world > 0 ? p->world : 1; q.rank = p->rank;
+        if (q.K < 13 || q.K % 2 == 0 || q.K > (q.flavour127 ? 127 : 63)) throw std::runtime_error("pgb200: K must be odd, 13..63 (63-mer flavour) or 13..127 (127-mer flavour)");
+        pgb200_engine* h = new pgb200_engine;
+        h->prm = q;
+        h->e = make_engine(q);
+        return h;
+    } catch (const std::exception& ex) {
+        g_err = ex.what();
+        return nullptr;
+    }
+}
+extern "C" void pgb200_destroy(pgb200_engine* e) {
+    if (!e) return;
+    delete e->e;
+    delete e;
+}
+extern "C" void* pgb200_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { g_err = "cudaHostAlloc failed"; return nullptr; }
+    return p;
+}
+extern "C" void pgb200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" int pgb200_feed_text(pgb200_engine* e, const char* text, size_t nbytes, int on_device, int fastq, uint64_t ord_base,
+                                uint64_t ord_stride, int reverse_seq, int maxlen) {
+    PG_TRY e->e->feed_text(text, nbytes, on_device != 0, fastq, ord_base, ord_stride, reverse_seq, maxlen); PG_CATCH
+}
+extern "C" uint64_t pgb200_last_chunk_records(pgb200_engine* e) { return e->e->last_chunk_records(); }
+extern "C" int pgb200_finish_pass1(pgb200_engine* e, pgb200_pass1_stats* st) {
+    PG_TRY
+    Pass1Stats s;
+    e->e->finish_pass1(&s);
+    if (st) {
+        st->records = s.records; st->reads_kept = s.reads_kept; st->instances = s.instances; st->distinct = s.distinct;
+        st->table_slots = s.table_slots; st->launches = s.launches; st->ms_decode = s.ms_decode; st->ms_insert = s.ms_insert;
+    }
+    PG_CATCH
+}
+extern "C" int pgb200_reset_pass1(pgb200_engine* e) { PG_TRY e->e->reset_pass1(); PG_CATCH }
+extern "C" int pgb200_sweeps(pgb200_engine* e, long long hist[256], uint64_t* linear_marked, uint64_t* removed) {
+    PG_TRY
+    SweepStats s;
+    e->e->sweeps(&s);
+    if (hist) memcpy(hist, s.hist, sizeof s.hist);
+    if (linear_marked) *linear_marked = s.linear;
+    if (removed) *removed = s.removed;
+    PG_CATCH
+}
+extern "C" int pgb200_build_layout(pgb200_engine* e) { PG_TRY e->e->build_layout(); PG_CATCH }
+extern "C" uint64_t pgb200_node_count(pgb200_engine* e) { return e->e->node_count(); }
+extern "C" int pgb200_dump_nodes(pgb200_engine* e, void* out) { PG_TRY e->e->dump_nodes(out); PG_CATCH }
+
+// ------------------------------------------------------------------------------------------------ file writers
+static void write_file(const std::string& name, const void* data, size_t n) {
+    FILE* f = fopen(name.c_str(), "wb");
+    if (!f) throw std::runtime_error("Cannot open " + name + ". Now exit to system...");   // ckopen, check.c:30-34
+    if (n && fwrite(data, 1, n, f) != n) { fclose(f); throw std::runtime_error("short write on " + name); }
+    fclose(f);
+}
+
+static void tip_lines(const TipStats& t, int K, int D) {
+    if (D == 0) {
+        fprintf(stderr, "Start to remove frequency-one-kmer tips shorter than %d.\n", 2 * K);
+        fprintf(stderr, "Total %llu tip(s) removed.\n", (unsigned long long)t.single_tips);
+        fprintf(stderr, "%llu linear node(s) marked.\n", (unsigned long long)t.single_relinear);
+    }
+    fprintf(stderr, "Start to remove tips with minority links.\n");
+    for (size_t i = 0; i < t.minor_cycles.size(); i++) fprintf(stderr, "%llu tip(s) removed in cycle %zu.\n", (unsigned long long)t.minor_cycles[i], i + 1);
+    fprintf(stderr, "Total %llu tip(s) removed.\n", (unsigned long long)t.minor_tips);
+    fprintf(stderr, "%llu linear node(s) marked.\n", (unsigned long long)t.minor_relinear);
+}
+
+extern "C" int pgb200_remove_tips(pgb200_engine* e, pgb200_graph_stats* st) {
+    PG_TRY
+    TipStats t;
+    e->e->remove_tips(&t);
+    tip_lines(t, e->prm.K, (int)(signed char)e->prm.D);
+    if (st) { st->single_tips = t.single_tips; st->minor_tips = t.minor_tips; }
+    PG_CATCH
+}
+extern "C" int pgb200_kmer2edges(pgb200_engine* e, const char* prefix, pgb200_graph_stats* st) {
+    PG_TRY
+    EdgeStats es;
+    std::string text;
+    e->e->build_edges(&es, &text);
+    // gzopen(name,"w") + gzwrite: same zlib, same default level => the same byte stream as the reference's gzprintf calls
+    std::string name = std::string(prefix) + ".edge.gz";
+    gzFile gz = gzopen(name.c_str(), "w");
+    if (!gz) throw std::runtime_error("Cannot open " + name);
+    size_t off = 0;
+    while (off < text.size()) {
+        size_t n = std::min<size_t>(text.size() - off, 1u << 30);
+        if (gzwrite(gz, text.data() + off, (unsigned)n) != (int)n) { gzclose(gz); throw std::runtime_error("gzwrite failed on " + name); }
+        off += n;
+    }
+    gzclose(gz);
+    fprintf(stderr, "%llu (%llu) edge(s) and %llu extra node(s) constructed.\n", (unsigned long long)es.num_ed, (unsigned long long)es.edges,
+            (unsigned long long)es.extra_nodes);
+    if (st) { st->num_ed = es.num_ed; st->edges = es.edges; st->extra_nodes = es.extra_nodes; }
+    PG_CATCH
+}
+extern "C" int pgb200_read2edge(pgb200_engine* e, const char* prefix, pgb200_graph_stats* st) {
+    PG_TRY
+    Pass2Stats ps;
+    std::string arcs, path, mark;
+    e->e->pass2(&ps, &arcs, &path, &mark);
+    write_file(std::string(prefix) + ".preArc", arcs.data(), arcs.size());
+    if (e->prm.repsTie) {
+        write_file(std::string(prefix) + ".path", path.data(), path.size());
+        write_file(std::string(prefix) + ".markOnEdge", mark.data(), mark.size());
+        fprintf(stderr, "%llu marker(s) output.\n", (unsigned long long)ps.markers);
+    }
+    fprintf(stderr, "Reads alignment done, %llu read(s) deleted, %llu pre-arc(s) added.\n", (unsigned long long)ps.deleted_reads,
+            (unsigned long long)ps.arcs);
+    if (st) { st->deleted_reads = ps.deleted_reads; st->arcs = ps.arcs; }
+    PG_CATCH
+}
+static uint64_t g_num_ed_for_basic = 0;
+extern "C" int pgb200_output_vertex(pgb200_engine* e, const char* prefix, pgb200_graph_stats* st) {
+    PG_TRY
+    std::string vt;
+    uint64_t nv = 0;
+    e->e->vertices(&vt, &nv);
+    write_file(std::string(prefix) + ".vertex", vt.data(), vt.size());
+    fprintf(stderr, "%llu vertex(es) output.\n", (unsigned long long)nv);
+    char buf[512];
+    uint64_t num_ed = st ? st->num_ed : g_num_ed_for_basic;
+    int n = snprintf(buf, sizeof buf, "VERTEX %llu K %d\n\nEDGEs %llu\n\nMaxReadLen %d MinReadLen %d MaxNameLen %d\n", (unsigned long long)nv,
+                     e->prm.K, (unsigned long long)num_ed, e->prm.max_rd_len, 0, 256);
+    write_file(std::string(prefix) + ".preGraphBasic", buf, n);
+    if (st) st->vertices = nv;
+    PG_CATCH
+}
+
+// ------------------------------------------------------------------------------------------------ config (lib.c)
+struct Lib {
+    int avg_ins = 0, asm_flag = 3, reverse = 0, rd_len_cutoff = 0;
+    std::vector<std::string> f[7];   // [1]=f1 [0]=f2 [2]=q1 [4]=q2 [3]=p [5]=f [6]=q
+};
+static bool split_column(const char* line, std::string& a, std::string& b) {   // splitColumn lib.c:70-108
+    int len = (int)strlen(line), i = 0, n = 0;
+    std::string* t[2] = {&a, &b};
+    a.clear(); b.clear();
+    while (i < len) {
+        if (line[i] >= 32 && line[i] <= 126 && line[i] != '=') {
+            while (i < len && line[i] >= 32 && line[i] <= 126 && line[i] != '=') t[n]->push_back(line[i++]);
+            if (++n == 2) return true;
+        }
+        i++;
+    }
+    return false;
+}
+static void scan_lib(const char* cfg, std::vector<Lib>& libs, int& max_rd_len) {
+    FILE* fp = fopen(cfg, "r");
+    if (!fp) { fprintf(stderr, "Cannot open %s. Now exit to system...\n", cfg); exit(-1); }
+    char line[1024];
+    std::string a, b;
+    max_rd_len = 0;
+    while (fgets(line, sizeof line, fp)) {
+        if (strncmp(line, "[LIB]", 5) == 0) { libs.emplace_back(); continue; }
+        if (!split_column(line, a, b)) continue;
+        if (libs.empty()) { if (a == "max_rd_len") max_rd_len = atoi(b.c_str()); continue; }   // only before the first [LIB] (lib.c:152-165)
+        Lib& L = libs.back();
+        if (a == "f1") L.f[1].push_back(b); else if (a == "f2") L.f[0].push_back(b);
+        else if (a == "q1") L.f[2].push_back(b); else if (a == "q2") L.f[4].push_back(b);
+        else if (a == "p") L.f[3].push_back(b); else if (a == "f") L.f[5].push_back(b); else if (a == "q") L.f[6].push_back(b);
+        else if (a == "b") { fprintf(stderr, "pgb200: BAM input (b=) is not supported by the GPU engine\n"); exit(-1); }
+        else if (a == "avg_ins") L.avg_ins = atoi(b.c_str()); else if (a == "reverse_seq") L.reverse = atoi(b.c_str());
+        else if (a == "asm_flags") L.asm_flag = atoi(b.c_str()); else if (a == "rd_len_cutoff") L.rd_len_cutoff = atoi(b.c_str());
+    }
+    fclose(fp);
+    if (libs.empty()) { fprintf(stderr, "Config file error: no [LIB] in file\n"); exit(-1); }
+    for (size_t i = 0; i < libs.size(); i++) {
+        if (libs[i].f[1].size() != libs[i].f[0].size()) { fprintf(stderr, "Config file error: the number of mark \"f1\" is not the same as \"f2\"!\n"); exit(-1); }
+        if (libs[i].f[2].size() != libs[i].f[4].size()) { fprintf(stderr, "Config file error: the number of mark \"q1\" is not the same as \"q2\"!\n"); exit(-1); }
+        bool pe = !libs[i].f[1].empty() || !libs[i].f[2].empty() || !libs[i].f[3].empty();
+        if (pe && libs[i].avg_ins == 0) { fprintf(stderr, "Config file error: PE reads need avg_ins in [LIB] %zu\n", i + 1); exit(-1); }
+    }
+    std::stable_sort(libs.begin(), libs.end(), [](const Lib& x, const Lib& y) { return x.avg_ins < y.avg_ins; });   // qsort by avg_ins, lib.c:505
+}
+
+// ------------------------------------------------------------------------------------------------ streaming a file into the engine
+// Chunks are cut at record boundaries on the host (only the tail of each chunk is inspected); the GPU does the parsing.
+static size_t last_record_start(const char* buf, size_t n, bool fastq) {
+    // returns the offset of the last position that starts a record, such that buf[0..off) holds whole records
+    if (n == 0) return 0;
+    size_t p = n;
+    for (;;) {
+        // find previous line start
+        if (p == 0) return 0;
+        size_t q = p - 1;
+        while (q > 0 && buf[q - 1] != '\n') q--;
+        // q is a line start
+        if (!fastq) { if (buf[q] == '>') return q; }
+        else if (buf[q] == '@') {
+            // a FASTQ header is followed two lines later by a '+' line; a quality line starting with '@' is followed
+            // two lines later by a sequence line, which never starts with '+'
+            const char* e1 = (const char*)memchr(buf + q, '\n', n - q);
+            if (e1) {
+                const char* e2 = (const char*)memchr(e1 + 1, '\n', n - (e1 + 1 - buf));
+                if (e2 && (size_t)(e2 + 1 - buf) < n && e2[1] == '+') return q;
+            }
+        }
+        p = q;
+    }
+}
+
+struct Feeder {
+    pgb200_engine* eng;
+    char* pin = nullptr;
+    size_t cap = 0;
+    ~Feeder() { if (pin) pgb200_host_free(pin); }
+    // streams one file; returns number of records
+    uint64_t run(const std::string& fn, bool fastq, uint64_t ord_base, uint64_t ord_stride, int reverse, int maxlen) {
+        fprintf(stderr, "Import reads from file:\n %s\n", fn.c_str());
+        FILE* f = fopen(fn.c_str(), "rb");
+        if (!f) { fprintf(stderr, "Cannot open %s. Now exit to system...\n", fn.c_str()); exit(-1); }
+        if (!pin) {
+            const char* env = getenv("PGB200_CHUNK_MB");
+            cap = (size_t)(env ? atoi(env) : 256) << 20;
+            pin = (char*)pgb200_host_alloc(cap + 16);
+            if (!pin) { fprintf(stderr, "pgb200: %s\n", pgb200_last_error()); exit(-1); }
+        }
+        uint64_t recs = 0;
+        size_t have = 0;
+        bool eof = false;
+        while (!eof || have) {
+            size_t got = eof ? 0 : fread(pin + have, 1, cap - have, f);
+            if (got == 0) eof = true;
+            have += got;
+            if (have == 0) break;
+            size_t cut;
+            if (eof) {
+                cut = have;
+            } else {
+                cut = last_record_start(pin, have, fastq);
+                if (cut == 0) {
+                    if (have == cap) { fprintf(stderr, "pgb200: a single record exceeds the %zu MB chunk\n", cap >> 20); exit(-1); }
+                    continue;
+                }
+            }
+            if (pgb200_feed_text(eng, pin, cut, 0, fastq, ord_base + recs * ord_stride, ord_stride, reverse, maxlen)) {
+                fprintf(stderr, "readseqInLib return error! please make sure input file is correct fastq/fasta file \n(%s)\n", pgb200_last_error());
+                exit(-1);
+            }
+            recs += pgb200_last_chunk_records(eng);
+            memmove(pin, pin + cut, have - cut);
+            have -= cut;
+        }
+        fclose(f);
+        return recs;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ the stage
+static void usage(int flavour127) {
+    fprintf(stderr, "\npregraph -s configFile -o outputGraph [-R] [-K kmer -p n_cpu -a initMemoryAssumption -d KmerFreqCutoff]\n");
+    fprintf(stderr, "  -s <string>      configFile: the config file of solexa reads\n");
+    fprintf(stderr, "  -o <string>      outputGraph: prefix of output graph file name\n");
+    fprintf(stderr, "  -K <int>         kmer(min 13, max %d): kmer size, [23]\n", flavour127 ? 127 : 63);
+    fprintf(stderr, "  -p <int>         n_cpu: number of reference hash sets (layout parameter of the GPU engine), [8]\n");
+    fprintf(stderr, "  -a <int>         initMemoryAssumption: memory assumption initialized to avoid further reallocation, unit GB, [0]\n");
+    fprintf(stderr, "  -R (optional)    output extra information for resolving repeats in contig step, [NO]\n");
+    fprintf(stderr, "  -d <int>         KmerFreqCutoff: kmers with frequency no larger than KmerFreqCutoff will be deleted, [0]\n");
+}
+
+static double now_s() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+
+extern "C" int pgb200_pregraph_main(int argc, char** argv, int flavour127) {
+    double t_all = now_s();
+    fprintf(stderr, "\n********************\nPregraph\n********************\n\n");
+    // ---- initenv (pregraph.c:142-220)
+    pgb200_params prm;
+    pgb200_default_params(&prm);
+    prm.flavour127 = flavour127;
+    std::string cfg, prefix;
+    int inp = 0, outp = 0, c;
+    optind = 1;
+    fprintf(stderr, "Parameters: pregraph ");
+    while ((c = getopt(argc, argv, "a:s:o:K:p:d:R")) != EOF) {
+        switch (c) {
+            case 's': fprintf(stderr, "-s %s ", optarg); inp = 1; cfg = optarg; break;
+            case 'o': fprintf(stderr, "-o %s ", optarg); outp = 1; prefix = optarg; break;
+            case 'K': fprintf(stderr, "-K %s ", optarg); prm.K = atoi(optarg); break;
+            case 'p': fprintf(stderr, "-p %s ", optarg); prm.P = atoi(optarg); break;
+            case 'R': prm.repsTie = 1; fprintf(stderr, "-R "); break;
+            case 'd': fprintf(stderr, "-d %s ", optarg); prm.D = atoi(optarg) >= 0 ? atoi(optarg) : 0; break;
+            case 'a': fprintf(stderr, "-a %s ", optarg); prm.initG = atoi(optarg); break;
+            default:
+                if (!inp || !outp) { usage(flavour127); exit(-1); }
+        }
+    }
+    fprintf(stderr, "\n\n");
+    if (!inp || !outp) { usage(flavour127); exit(-1); }
+    // ---- K fix-ups (pregraph.c:71-97)
+    if (prm.K % 2 == 0) { prm.K++; fprintf(stderr, "K should be an odd number.\n"); }
+    if (prm.K < 13) { prm.K = 13; fprintf(stderr, "K should not be less than 13.\n"); }
+    else if (prm.K > (flavour127 ? 127 : 63)) { prm.K = flavour127 ? 127 : 63; fprintf(stderr, "K should not be greater than %d.\n", prm.K); }
+    if (const char* v = getenv("PGB200_DEVICE")) prm.device = atoi(v);
+    if (const char* v = getenv("PGB200_TABLE_SLOTS")) prm.table_slots = strtoull(v, nullptr, 10);
+    if (const char* v = getenv("PGB200_VERBOSE")) prm.verbose = atoi(v);
+
+    // ---- pass 1 (prlRead2HashTable)
+    double t0 = now_s();
+    std::vector<Lib> libs;
+    int max_rd_len = 0;
+    scan_lib(cfg.c_str(), libs, max_rd_len);
+    if (!max_rd_len) max_rd_len = 100;   // prlHashReads.c:326-329
+    prm.max_rd_len = max_rd_len;
+    fprintf(stderr, "In %s, %d lib(s), maximum read length %d, maximum name length %d.\n\n", cfg.c_str(), (int)libs.size(), max_rd_len, 256);
+    pgb200_engine* eng = pgb200_create(&prm);
+    if (!eng) { fprintf(stderr, "pgb200: %s\n", pgb200_last_error()); exit(-1); }
+    auto die = [&](const char* what) { fprintf(stderr, "pgb200: %s failed: %s\n", what, pgb200_last_error()); exit(-1); };
+    fprintf(stderr, "%d thread(s) initialized.\n", prm.P);
+    uint64_t ord_next = 0, n_reads = 0;
+    {
+        Feeder fd;
+        fd.eng = eng;
+        for (const Lib& L : libs) {
+            if (L.asm_flag != 1 && L.asm_flag != 3) continue;                           // nextValidIndex, readseq1by1.c:601
+            int cut = (L.rd_len_cutoff > 0 && L.rd_len_cutoff < max_rd_len) ? L.rd_len_cutoff : max_rd_len;   // prlHashReads.c:921-928
+            for (int type = 1; type <= 6; type++) {
+                if (type == 4) continue;
+                bool fq = (type == 2 || type == 6);
+                for (size_t fi = 0; fi < L.f[type].size(); fi++) {
+                    if (type <= 2) {
+                        // mates interleave r1,r2,r1,r2 (prlHashReads.c:480-583): ordinal = base + 2*pair + mate
+                        uint64_t n1 = fd.run(L.f[type][fi], fq, ord_next, 2, L.reverse, cut);
+                        uint64_t n2 = fd.run(L.f[type == 1 ? 0 : 4][fi], fq, ord_next + 1, 2, L.reverse, cut);
+                        if (n1 != n2) { fprintf(stderr, "pgb200: mate files hold different numbers of reads (%llu vs %llu): unsupported\n", (unsigned long long)n1, (unsigned long long)n2); exit(-1); }
+                        ord_next += 2 * n1; n_reads += 2 * n1;
+                    } else {
+                        uint64_t n = fd.run(L.f[type][fi], fq, ord_next, 1, L.reverse, cut);
+                        ord_next += n; n_reads += n;
+                    }
+                }
+            }
+        }
+    }
+    pgb200_pass1_stats p1;
+    if (pgb200_finish_pass1(eng, &p1)) die("pass 1");
+    double t1 = now_s();
+    fprintf(stderr, "Time spent on hashing reads: %ds, %lld read(s) processed.\n", (int)(t1 - t0), (long long)n_reads);
+    fprintf(stderr, "%lli node(s) allocated, %lli kmer(s) in reads, %lli kmer(s) processed.\n", (long long)p1.distinct, (long long)p1.instances, (long long)p1.instances);
+    fprintf(stderr, "[pgb200] pass 1: %.3f s wall, decode %.1f ms + insert %.1f ms on the GPU, table %llu slots\n", t1 - t0, p1.ms_decode, p1.ms_insert, (unsigned long long)p1.table_slots);
+    fprintf(stderr, "done hashing nodes\n");
+    long long hist[256];
+    uint64_t lin = 0, rem = 0;
+    if (pgb200_sweeps(eng, hist, &lin, &rem)) die("sweeps");
+    if ((signed char)prm.D) fprintf(stderr, "%llu kmer(s) removed.\n", (unsigned long long)rem);
+    fprintf(stderr, "%llu linear node(s) marked.\n", (unsigned long long)lin);
+    {
+        std::string s;
+        char b[32];
+        for (int i = 1; i < 256; i++) { snprintf(b, sizeof b, "%lld\n", hist[i]); s += b; }   // freqStat, prlHashReads.c:1104-1132
+        try { write_file(prefix + ".kmerFreq", s.data(), s.size()); } catch (const std::exception& ex) { fprintf(stderr, "%s\n", ex.what()); exit(-1); }
+    }
+    fprintf(stderr, "Time spent on pre-graph construction: %ds.\n\n", (int)(now_s() - t0));
+    if (getenv("PGB200_PASS1_ONLY")) { pgb200_destroy(eng); return 0; }
+
+    // ---- layout + tips (removeSingleTips / removeMinorTips)
+    t0 = now_s();
+    if (pgb200_build_layout(eng)) die("layout");
+    pgb200_graph_stats gs;
+    memset(&gs, 0, sizeof gs);
+    if (pgb200_remove_tips(eng, &gs)) die("tips");
+    fprintf(stderr, "Time spent on removing tips: %ds.\n\n", (int)(now_s() - t0));
+    // ---- edges (kmer2edges)
+    t0 = now_s();
+    if (pgb200_kmer2edges(eng, prefix.c_str(), &gs)) die("edges");
+    fprintf(stderr, "Time spent on constructing edges: %ds.\n\n", (int)(now_s() - t0));
+    // ---- pass 2 (prlRead2edge)
+    t0 = now_s();
+    if (pgb200_read2edge(eng, prefix.c_str(), &gs)) die("pass 2");
+    fprintf(stderr, "Time spent on aligning reads: %ds.\n\n", (int)(now_s() - t0));
+    if (pgb200_output_vertex(eng, prefix.c_str(), &gs)) die("vertex output");
+    pgb200_destroy(eng);
+    fprintf(stderr, "Overall time spent on constructing pre-graph: %dm.\n\n", (int)(now_s() - t_all) / 60);
+    return 0;
+}
+
+extern "C" int call_pregraph(int argc, char** argv) {
+    const char* f = getenv("PGB200_FLAVOUR");
+    return pgb200_pregraph_main(argc, argv, f && atoi(f) == 127 ? 1 : 0);
+}

@@ -1,0 +1,462 @@
+// pass1.cu -- pass 1 of pregraph on the GPU: text -> 2-bit reads -> canonical k-mers -> table insert/count,
+// then the per-entry sweeps (delow, mark-linear, kmerFreq histogram).
+//
+// Replaces (reference file:line, standardPregraph/):
+//   K1  readseqInBuf / readseqfq (readseq1by1.c:138-209, 279-360), reverse2k (:788-802)    -> k_decode_pack
+//   K2  chopKmer4read (prlHashReads.c:163-259)                                              -> k_chop_insert (rolling part)
+//   K3  threadRoutine sig 1 + put_kmerset (prlHashReads.c:79-90, newhash.c:473-528)         -> k_chop_insert (insert part)
+//   K4  thread_delow, thread_mark, freqStat (prlHashReads.c:953-996, 1020-1077, 1104-1132)  -> k_sweep
+// Design differences that matter: no owner filter (the reference makes every thread scan the whole batch and keep
+// hash % P == id); the CRC set hash is not computed per instance at all -- it only defines the reference's iteration
+// order and is evaluated once per DISTINCT k-mer in layout.cu.
+#include "engine_impl.cuh"
+#include "scan.cuh"
+
+namespace pgb {
+
+// ------------------------------------------------------------------------------------------------ K1: line index
+// element = one 16-byte group of the text; value = number of '\n' in it
+struct NlIn {
+    const uint4* text;
+    u64 nbytes;
+    __device__ __forceinline__ unsigned mask16(u64 i) const {
+        uint4 v = __ldg(text + i);
+        unsigned m = 0;
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            unsigned r = __vcmpeq4(w[k], 0x0A0A0A0Au) & 0x01010101u;   // exact per-byte compare
+            m |= ((r | (r >> 7) | (r >> 14) | (r >> 21)) & 0xFu) << (4 * k);
+        }
+        u64 rem = nbytes - i * 16;
+        if (rem < 16) m &= (1u << rem) - 1;
+        return m;
+    }
+    __device__ u64 operator()(u64 i) const { return __popc(mask16(i)); }
+};
+// newline number g (0-based) at byte `pos`: line g+1 starts at pos+1.  Sequence line of record r is line lpr*r+1.
+struct NlOut {
+    NlIn in;
+    u64* seq_start;
+    u64* seq_end;
+    u64 n_rec;
+    int lpr;
+    __device__ void operator()(u64 i, u64 prefix, u64 v) const {
+        if (!v) return;
+        unsigned m = in.mask16(i);
+        u64 g = prefix;
+        while (m) {
+            int b = __ffs(m) - 1;
+            m &= m - 1;
+            u64 line = g + 1, pos = i * 16 + b;
+            u64 r = line / lpr, k = line - r * lpr;
+            if (k == 1 && r < n_rec) seq_start[r] = pos + 1;
+            if (k == 2 && r < n_rec) seq_end[r] = pos;
+            g++;
+        }
+    }
+};
+struct NlCountOut {
+    __device__ void operator()(u64, u64, u64) const {}
+};
+
+// ------------------------------------------------------------------------------------------------ K1: decode + pack
+// One warp per record.  Base code = (ch & 6) >> 1 for letters (A0 C1 T2 G3, N->3), '.' -> 0, every other byte is dropped;
+// only the first min(linelen, maxlen) characters of the sequence line are considered (readseq1by1.c:177-200).
+// reverse_seq: whole-read reverse complement (reverse2k).  Output: LSB-first 2-bit packing, W64 words per read.
+__device__ __forceinline__ bool is_base_char(unsigned c) { return ((c | 0x20u) - 'a') < 26u || c == '.'; }
+__device__ __forceinline__ unsigned base_code(unsigned c) { return c == '.' ? 0u : ((c & 6u) >> 1); }
+
+__global__ void __launch_bounds__(256) k_decode_pack(const unsigned char* __restrict__ text, const u64* __restrict__ seq_start,
+                                                     const u64* __restrict__ seq_end, u64 n_rec, int maxlen, int reverse, int K,
+                                                     int W64, u64* __restrict__ words, u32* __restrict__ lens, u64* counters) {
+    const int lane = threadIdx.x & 31;
+    const u64 warp0 = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    u64 inst = 0, kept = 0;
+    for (u64 r = warp0; r < n_rec; r += nwarps) {
+        const u64 s = seq_start[r];
+        u64 e = seq_end[r];
+        int raw = e > s ? (int)min((u64)(e - s), (u64)0x7fffffff) : 0;
+        int use = raw < maxlen ? raw : maxlen;
+        // count valid characters
+        int n = 0;
+        bool clean = true;
+        for (int b = 0; b < use; b += 32) {
+            int i = b + lane;
+            bool v = i < use && is_base_char(text[s + i]);
+            unsigned bal = __ballot_sync(0xffffffffu, v);
+            unsigned want = (use - b) >= 32 ? 0xffffffffu : ((1u << (use - b)) - 1);
+            clean = clean && (bal == want);
+            n += __popc(bal);
+        }
+        u64* out = words + r * (u64)W64;
+        if (clean) {
+            for (int w = 0; w < W64; w++) {
+                int oi = w * 32 + lane;   // output base index handled by this lane
+                unsigned lo = 0, hi = 0;
+                if (oi < n) {
+                    int ii = reverse ? n - 1 - oi : oi;
+                    unsigned c = base_code(text[s + ii]) ^ (reverse ? 2u : 0u);
+                    if (lane < 16) lo = c << (2 * lane); else hi = c << (2 * (lane - 16));
+                }
+                lo = __reduce_or_sync(0xffffffffu, lo);
+                hi = __reduce_or_sync(0xffffffffu, hi);
+                if (lane == 0) out[w] = (u64)lo | ((u64)hi << 32);
+            }
+        } else {
+            // rare: a byte inside the line is not a letter ('\r', digits, ...): compact with ballots + global atomicOr
+            for (int w = lane; w < W64; w += 32) out[w] = 0;
+            __syncwarp();
+            int pos0 = 0;
+            for (int b = 0; b < use; b += 32) {
+                int i = b + lane;
+                unsigned ch = i < use ? text[s + i] : 0;
+                bool v = i < use && is_base_char(ch);
+                unsigned bal = __ballot_sync(0xffffffffu, v);
+                if (v) {
+                    int p = pos0 + __popc(bal & ((1u << lane) - 1));
+                    int oi = reverse ? n - 1 - p : p;
+                    u64 c = base_code(ch) ^ (reverse ? 2u : 0u);
+                    atomicOr(&out[oi >> 5], c << (2 * (oi & 31)));
+                }
+                pos0 += __popc(bal);
+            }
+        }
+        if (lane == 0) {
+            lens[r] = (u32)n;
+            if (n >= K + 1) { inst += (u64)(n - K + 1); kept++; }   // reads shorter than K+1 are skipped (prlHashReads.c:504,642)
+        }
+    }
+    // block-level aggregation of the counters
+    __shared__ u64 s_inst, s_kept;
+    if (threadIdx.x == 0) { s_inst = 0; s_kept = 0; }
+    __syncthreads();
+    if (lane == 0 && (inst | kept)) { atomicAdd(&s_inst, inst); atomicAdd(&s_kept, kept); }
+    __syncthreads();
+    if (threadIdx.x == 0 && (s_inst | s_kept)) { atomicAdd(&counters[C_INSTANCES], s_inst); atomicAdd(&counters[C_KEPT], s_kept); }
+}
+
+// ------------------------------------------------------------------------------------------------ K2+K3: chop + insert
+// One thread per read: roll the forward k-mer (nextKmer) and its reverse complement (prevKmer on the complement strand)
+// one base at a time, pick the canonical one, derive the left/right neighbour codes in the canonical orientation
+//  and apply the instance to the table.  rank = (read ordinal << 16) | position.
+template <int NW>
+__global__ void __launch_bounds__(256) k_chop_insert(Table<NW> tab, KParams<NW> kp, const u64* __restrict__ words,
+                                                     const u32* __restrict__ lens, u64 n_rec, int W64, u64 ord_base, u64 ord_stride,
+                                                     int world, int myrank, u64* counters) {
+    __shared__ unsigned s_new;
+    if (threadIdx.x == 0) s_new = 0;
+    __syncthreads();
+    const int K = kp.K;
+    unsigned my_new = 0;
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += (u64)gridDim.x * blockDim.x) {
+        const int L = (int)lens[r];
+        if (L < K + 1) continue;
+        const u64* wp = words + r * (u64)W64;
+        const u64 rank_base = (ord_base + r * ord_stride) << 16;
+        Kmer<NW> fwd = kzero<NW>(), rc = kzero<NW>();
+        u64 cur = wp[0];
+        unsigned c = (unsigned)(cur & 3);          // base i
+        for (int i = 0; i < L; i++) {
+            // look ahead one base (needed as the right neighbour of the k-mer ending at i)
+            unsigned cn = 4;
+            if (i + 1 < L) {
+                if (((i + 1) & 31) == 0) cur = wp[(i + 1) >> 5];
+                cn = (unsigned)((cur >> (2 * ((i + 1) & 31))) & 3);
+            }
+            unsigned dropped = kfirst(fwd, kp);    // base j-1 (valid when j >= 1)
+            fwd = knext(fwd, c, kp);
+            rc = kprev(rc, c ^ 2u, kp);
+            int j = i - K + 1;
+            if (j >= 0) {
+                unsigned pv = j > 0 ? dropped : 4u;
+                bool sm = kless(fwd, rc);          // KmerSmaller(word, bal_word); tie -> rc branch
+                Kmer<NW> canon = sm ? fwd : rc;
+                unsigned left = sm ? pv : (cn < 4 ? (cn ^ 2u) : 4u);
+                unsigned right = sm ? cn : (pv < 4 ? (pv ^ 2u) : 4u);
+                if (world > 1 && (int)(mix64(table_hash(canon) ^ 0x5bd1e995ull) % (u64)world) != myrank) { c = cn; continue; }
+                bool claimed;
+                u64 idx = table_find_or_claim(tab, canon, &claimed);
+                my_new += claimed;
+                slot_apply(tab.slots + idx, left, right, rank_base | (u64)j);
+            }
+            c = cn;
+        }
+    }
+    if (my_new) atomicAdd(&s_new, my_new);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_new) atomicAdd(&counters[C_DISTINCT], (u64)s_new);
+}
+
+// ------------------------------------------------------------------------------------------------ table management
+template <int NW>
+__global__ void k_rehash(Table<NW> oldt, Table<NW> newt) {
+    u64 n = oldt.mask + 1;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const Slot<NW>* s = oldt.slots + i;
+        if (!slot_occupied(s)) continue;
+        Kmer<NW> k = slot_key(s);
+        bool claimed;
+        u64 idx = table_find_or_claim(newt, k, &claimed);
+        newt.slots[idx].payload = s->payload;
+        newt.slots[idx].aux = s->aux;
+    }
+}
+
+static u64 next_pow2(u64 x) { u64 p = 1; while (p < x) p <<= 1; return p; }
+
+template <int NW>
+void EngineT<NW>::alloc_table(u64 cap) {
+    tab_buf_.alloc(cap * sizeof(Slot<NW>));
+    PG_CUDA(cudaMemsetAsync(tab_buf_.p, 0xFF, cap * sizeof(Slot<NW>), st_));
+    tab_.slots = tab_buf_.template as<Slot<NW>>();
+    tab_.mask = cap - 1;
+    cap_ = cap;
+}
+
+template <int NW>
+void EngineT<NW>::grow_table(u64 new_cap) {
+    if (prm_.verbose) fprintf(stderr, "[pgb200] growing k-mer table %llu -> %llu slots\n", cap_, new_cap);
+    DevBuf nb;
+    nb.alloc(new_cap * sizeof(Slot<NW>));
+    PG_CUDA(cudaMemsetAsync(nb.p, 0xFF, new_cap * sizeof(Slot<NW>), st_));
+    Table<NW> nt{nb.template as<Slot<NW>>(), new_cap - 1};
+    k_rehash<NW><<<148 * 8, 256, 0, st_>>>(tab_, nt);
+    PG_CUDA(cudaGetLastError());
+    sync();
+    std::swap(tab_buf_.p, nb.p);
+    std::swap(tab_buf_.bytes, nb.bytes);
+    tab_ = nt;
+    cap_ = new_cap;
+}
+
+template <int NW>
+void EngineT<NW>::ensure_table(u64 incoming) {
+    if (!tab_.slots) {
+        u64 want = prm_.table_slots;
+        if (!want) {
+            if (prm_.initG) {
+                // the reference's own budget: P sets of the static prime size (prlHashReads.c:369-390)
+                want = (u64)prm_.P * ref_static_set_size(prm_.initG, prm_.P, prm_.flavour127 != 0);
+                want = want + want / 4;
+            } else {
+                want = 1ull << 24;
+            }
+        }
+        u64 cap = next_pow2(want < 1024 ? 1024 : want);
+        alloc_table(cap);
+    }
+    read_counters();
+    u64 need = h_cnt_[C_DISTINCT] + incoming;   // every incoming instance could be a new key
+    if ((double)need <= 0.80 * (double)cap_) return;
+    u64 cap = cap_;
+    while ((double)need > 0.80 * (double)cap) cap <<= 1;
+    size_t free_b = 0, total_b = 0;
+    PG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    while (cap > cap_ && cap * sizeof(Slot<NW>) + (1ull << 30) > free_b) cap >>= 1;
+    if (cap > cap_) { grow_table(cap); return; }
+    if ((double)need > 0.97 * (double)cap_)
+        throw std::runtime_error("pgb200: k-mer table cannot grow further (out of HBM); use more GPUs or a smaller batch");
+}
+
+// ------------------------------------------------------------------------------------------------ feed_text
+template <int NW>
+void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int fastq, uint64_t ord_base, uint64_t ord_stride,
+                            int reverse_seq, int maxlen) {
+    last_records_ = 0;
+    if (nbytes == 0) return;
+    PG_CUDA(cudaSetDevice(prm_.device));
+    PG_CUDA(cudaEventRecord(ev_[0], st_));
+    const unsigned char* d_text;
+    if (on_device) {
+        if ((uintptr_t)text & 15) throw std::runtime_error("pgb200: device text must be 16-byte aligned");
+        d_text = reinterpret_cast<const unsigned char*>(text);
+    } else {
+        text_buf_.ensure(nbytes + 16);
+        PG_CUDA(cudaMemcpyAsync(text_buf_.p, text, nbytes, cudaMemcpyHostToDevice, st_));
+        d_text = text_buf_.template as<unsigned char>();
+    }
+    if (maxlen > prm_.max_rd_len) maxlen = prm_.max_rd_len;
+    const int lpr = fastq ? 4 : 2;
+    const u64 groups = (nbytes + 15) / 16;
+    scan_buf_.ensure(scan_scratch_elems(groups) * sizeof(u64));
+    NlIn in{reinterpret_cast<const uint4*>(d_text), (u64)nbytes};
+    // pass A: count lines
+    device_scan(in, NlCountOut{}, groups, scan_buf_.template as<u64>(), d_cnt_ + C_MISC0, st_);
+    read_counters();
+    u64 n_lines = h_cnt_[C_MISC0];
+    // a final line without '\n' still counts (the reference's FASTQ path tolerates it; its FASTA path does not)
+    unsigned char lastc;
+    PG_CUDA(cudaMemcpyAsync(&lastc, d_text + nbytes - 1, 1, cudaMemcpyDeviceToHost, st_));
+    sync();
+    bool open_tail = lastc != '\n';
+    u64 n_rec = (n_lines + (open_tail ? 1 : 0)) / lpr;
+    if ((n_lines + (open_tail ? 1 : 0)) % lpr != 0)
+        throw std::runtime_error("pgb200: text chunk does not hold whole FASTA/FASTQ records (line count not a multiple of 2/4)");
+    if (n_rec == 0) return;
+    line_buf_.ensure(2 * n_rec * sizeof(u64));
+    u64* seq_start = line_buf_.template as<u64>();
+    u64* seq_end = seq_start + n_rec;
+    if (open_tail) {
+        // only FASTQ can end without newline inside the quality line; the sequence line end is always a real '\n'
+        PG_CUDA(cudaMemsetAsync(seq_end, 0, n_rec * sizeof(u64), st_));
+    }
+    device_scan(in, NlOut{in, seq_start, seq_end, n_rec, lpr}, groups, scan_buf_.template as<u64>(), d_cnt_ + C_MISC0, st_);
+    if (open_tail && !fastq) {
+        u64 e = nbytes;
+        PG_CUDA(cudaMemcpyAsync(seq_end + n_rec - 1, &e, sizeof e, cudaMemcpyHostToDevice, st_));
+        sync();
+    }
+
+    ReadChunk ch;
+    ch.n_rec = n_rec;
+    ch.ord_base = ord_base;
+    ch.ord_stride = ord_stride;
+    PG_CUDA(cudaMalloc(&ch.words, n_rec * (u64)W64_ * sizeof(u64)));
+    PG_CUDA(cudaMalloc(&ch.len, n_rec * sizeof(u32)));
+    chunks_.push_back(ch);
+    {
+        u64 warps = n_rec;
+        unsigned blocks = (unsigned)std::min<u64>((warps + 7) / 8, 148ull * 64);
+        k_decode_pack<<<blocks, 256, 0, st_>>>(d_text, seq_start, seq_end, n_rec, maxlen, reverse_seq, prm_.K, W64_, ch.words, ch.len,
+                                               d_cnt_);
+        PG_CUDA(cudaGetLastError());
+    }
+    PG_CUDA(cudaEventRecord(ev_[1], st_));
+    // table capacity for the worst case of this chunk
+    u64 before_inst = h_cnt_[C_INSTANCES];
+    ensure_table(0);   // creates the table on first use, refreshes h_cnt_ (decode is complete after this sync)
+    u64 chunk_inst = h_cnt_[C_INSTANCES] - before_inst;
+    ensure_table(chunk_inst);
+    PG_CUDA(cudaEventRecord(ev_[2], st_));
+    {
+        unsigned blocks = (unsigned)std::min<u64>((n_rec + 255) / 256, 148ull * 32);
+        k_chop_insert<NW><<<blocks, 256, 0, st_>>>(tab_, kp_, ch.words, ch.len, n_rec, W64_, ord_base, ord_stride, prm_.world, prm_.rank,
+                                                   d_cnt_);
+        PG_CUDA(cudaGetLastError());
+    }
+    PG_CUDA(cudaEventRecord(ev_[3], st_));
+    sync();
+    float ms;
+    PG_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1])); p1_.ms_decode += ms;
+    PG_CUDA(cudaEventElapsedTime(&ms, ev_[2], ev_[3])); p1_.ms_insert += ms;
+    p1_.launches += 8;
+    last_records_ = n_rec;
+    total_records_ += n_rec;
+}
+
+template <int NW>
+void EngineT<NW>::finish_pass1(Pass1Stats* st) {
+    read_counters();
+    p1_.records = total_records_;
+    p1_.reads_kept = h_cnt_[C_KEPT];
+    p1_.instances = h_cnt_[C_INSTANCES];
+    p1_.distinct = h_cnt_[C_DISTINCT];
+    p1_.table_slots = cap_;
+    n_nodes_ = p1_.distinct;
+    if (st) *st = p1_;
+}
+
+template <int NW>
+void EngineT<NW>::reset_pass1() {
+    sync();
+    for (auto& c : chunks_) { cudaFree(c.words); cudaFree(c.len); }
+    chunks_.clear();
+    total_records_ = 0;
+    p1_ = Pass1Stats();
+    PG_CUDA(cudaMemsetAsync(d_cnt_, 0, C_COUNT * sizeof(u64), st_));
+    if (tab_.slots) PG_CUDA(cudaMemsetAsync(tab_buf_.p, 0xFF, cap_ * sizeof(Slot<NW>), st_));
+    order_buf_.release();
+    n_nodes_ = 0;
+    sync();
+    h_cnt_[C_DISTINCT] = h_cnt_[C_INSTANCES] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ K4: sweeps
+// delow (thread_delow): zero every link counter <= D, deleted=1 if nothing is left.  mark (thread_mark): linear=1 iff exactly
+// one non-zero left and one non-zero right link (NO deleted check there); histogram of cov.  All per-entry => one pass.
+template <int NW>
+__global__ void __launch_bounds__(256) k_sweep(Table<NW> tab, int D, u64* hist, u64* counters) {
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned s_lin, s_rem;
+    s_hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { s_lin = 0; s_rem = 0; }
+    __syncthreads();
+    u64 n = tab.mask + 1;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        Slot<NW>* s = tab.slots + i;
+        if (!slot_occupied(s)) continue;
+        u64 p = s->payload;
+        if (D > 0) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                unsigned l = pl_l(p, c), r = pl_r(p, c);
+                if (l > 0 && l <= (unsigned)D) p = pl_clear_l(p, c);
+                if (r > 0 && r <= (unsigned)D) p = pl_clear_r(p, c);
+            }
+            if ((p & PL_LLINKS_MASK) == 0 && (p & PL_RLINKS_MASK) == 0) { p |= PL_DELETED; atomicAdd(&s_rem, 1u); }
+        }
+        atomicAdd(&s_hist[pl_cov(p)], 1u);
+        if (pl_nl(p) == 1 && pl_nr(p) == 1) { p |= PL_LINEAR; atomicAdd(&s_lin, 1u); }
+        s->payload = p;
+    }
+    __syncthreads();
+    if (s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (u64)s_hist[threadIdx.x]);
+    if (threadIdx.x == 0) {
+        if (s_lin) atomicAdd(&counters[C_LINEAR], (u64)s_lin);
+        if (s_rem) atomicAdd(&counters[C_REMOVED], (u64)s_rem);
+    }
+}
+
+template <int NW>
+void EngineT<NW>::sweeps(SweepStats* st) {
+    DevBuf hist;
+    hist.alloc(256 * sizeof(u64));
+    PG_CUDA(cudaMemsetAsync(hist.p, 0, 256 * sizeof(u64), st_));
+    PG_CUDA(cudaMemsetAsync(d_cnt_ + C_LINEAR, 0, 2 * sizeof(u64), st_));
+    int D = (int)(signed char)prm_.D;   // deLowKmer is a `char` (inc/global.h:67)
+    k_sweep<NW><<<148 * 8, 256, 0, st_>>>(tab_, D, hist.template as<u64>(), d_cnt_);
+    PG_CUDA(cudaGetLastError());
+    u64 h[256];
+    PG_CUDA(cudaMemcpyAsync(h, hist.p, sizeof h, cudaMemcpyDeviceToHost, st_));
+    read_counters();
+    for (int i = 0; i < 256; i++) st->hist[i] = (long long)h[i];
+    st->linear = h_cnt_[C_LINEAR];
+    st->removed = h_cnt_[C_REMOVED];
+}
+
+// ------------------------------------------------------------------------------------------------ ctor / dtor
+template <int NW>
+EngineT<NW>::EngineT(const PgParams& p) : prm_(p) {
+    PG_CUDA(cudaSetDevice(p.device));
+    kp_ = make_kparams<NW>(p.K);
+    PG_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    for (auto& e : ev_) PG_CUDA(cudaEventCreate(&e));
+    PG_CUDA(cudaMalloc(&d_cnt_, C_COUNT * sizeof(u64)));
+    PG_CUDA(cudaMemsetAsync(d_cnt_, 0, C_COUNT * sizeof(u64), st_));
+    PG_CUDA(cudaHostAlloc(&h_cnt_, C_COUNT * sizeof(u64), cudaHostAllocDefault));
+    for (int i = 0; i < C_COUNT; i++) h_cnt_[i] = 0;
+    W64_ = (p.max_rd_len + 31) / 32;
+    if (W64_ < 1) W64_ = 1;
+    sync();
+}
+
+template <int NW>
+EngineT<NW>::~EngineT() {
+    cudaStreamSynchronize(st_);
+    for (auto& c : chunks_) { cudaFree(c.words); cudaFree(c.len); }
+    if (d_cnt_) cudaFree(d_cnt_);
+    if (h_cnt_) cudaFreeHost(h_cnt_);
+    for (auto& e : ev_) if (e) cudaEventDestroy(e);
+    if (st_) cudaStreamDestroy(st_);
+}
+
+template class EngineT<2>;
+template class EngineT<4>;
+
+IEngine* make_engine(const PgParams& p) {
+    if (p.K <= 63) return new EngineT<2>(p);
+    return new EngineT<4>(p);
+}
+
+}   // namespace pgb
