@@ -48,10 +48,12 @@ struct NlOut {
         while (m) {
             int b = __ffs(m) - 1;
             m &= m - 1;
-            u64 line = g + 1, pos = i * 16 + b;
-            u64 r = line / lpr, k = line - r * lpr;
-            if (k == 1 && r < n_rec) seq_start[r] = pos + 1;
-            if (k == 2 && r < n_rec) seq_end[r] = pos;
+            u64 pos = i * 16 + b;
+            // newline g ends line g and line g+1 starts at pos+1; the sequence line of record r is line lpr*r + 1
+            u64 r0 = g / lpr;
+            if (g - r0 * lpr == 1 && r0 < n_rec) seq_end[r0] = pos;
+            u64 r1 = (g + 1) / lpr;
+            if ((g + 1) - r1 * lpr == 1 && r1 < n_rec) seq_start[r1] = pos + 1;
             g++;
         }
     }

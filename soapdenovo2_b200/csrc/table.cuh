@@ -88,14 +88,21 @@ struct Table {
 
 #if defined(__CUDACC__)
 
+// Table loads are STRONG (relaxed, gpu scope): a weak ld.global may legally be hoisted out of a polling loop by ptxas
+// (observed: the publish-wait below was turned into a single load, producing duplicate 256-bit keys on the GPU).
 PG_D U128 ldcg128(const void* p) {
     U128 r;
-    asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(r.a), "=l"(r.b) : "l"(p));
+    asm volatile("ld.relaxed.gpu.global.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(r.a), "=l"(r.b) : "l"(p) : "memory");
     return r;
 }
 PG_D u64 ldcg64(const void* p) {
     u64 r;
-    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(r) : "l"(p));
+    asm volatile("ld.relaxed.gpu.global.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");
+    return r;
+}
+PG_D u64 ldacq64(const void* p) {
+    u64 r;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");
     return r;
 }
 PG_D void stcg128(void* p, U128 v) { asm volatile("st.global.cg.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(v.a), "l"(v.b) : "memory"); }
@@ -144,10 +151,10 @@ PG_D u64 table_find_or_claim<4>(const Table<4>& t, const Kmer<4>& k, bool* claim
             hi = old;
         }
         if ((hi.a & ~BUSY_BIT) == k.w[0] && hi.b == k.w[1]) {
-            while (hi.a & BUSY_BIT) hi.a = ldcg64(&s->key[0]);   // wait for the lower half to be published
-            __threadfence();
+            // wait (acquire) until the lower half has been published, then compare it
+            do { hi.a = ldacq64(&s->key[0]); } while (hi.a & BUSY_BIT);
             U128 lo = ldcg128(&s->key[2]);
-            if (lo.a == k.w[2] && lo.b == k.w[3]) return idx;
+            if (hi.a == k.w[0] && lo.a == k.w[2] && lo.b == k.w[3]) return idx;
         }
         idx = (idx + 1) & t.mask;
     }
