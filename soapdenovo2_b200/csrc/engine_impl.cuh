@@ -6,6 +6,7 @@
 #include "table.cuh"
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -78,6 +79,7 @@ public:
     cudaStream_t st_ = nullptr;
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     int W64_ = 0;   // packed words per read
+    int l2gran_mode_ = 0;   // PGB200_L2GRAN: 0 default, 1 = 32 B globally, 2 = 32 B only around k_chop_insert
 
     std::vector<ReadChunk> chunks_;
     uint64_t last_records_ = 0, total_records_ = 0;

@@ -11,6 +11,7 @@
 // order and is evaluated once per DISTINCT k-mer in layout.cu.
 #include "engine_impl.cuh"
 #include "scan.cuh"
+#include <ctime>
 
 namespace pgb {
 
@@ -142,48 +143,62 @@ __global__ void __launch_bounds__(256) k_decode_pack(const unsigned char* __rest
 // One thread per read: roll the forward k-mer (nextKmer) and its reverse complement (prevKmer on the complement strand)
 // one base at a time, pick the canonical one, derive the left/right neighbour codes in the canonical orientation
 //  and apply the instance to the table.  rank = (read ordinal << 16) | position.
+// (A software-prefetch variant -- prefetch.global.L2 of the home slot 1..8 positions ahead, instances parked in a shared
+//  memory ring -- was measured and dropped: 38.6 ms vs 28.0 ms per 5.3e8 instances at every distance; the kernel is bound
+//  by the random-sector rate of L2/HBM, not by exposed latency.  profiles/r01_insert_ncu.md.)
+constexpr int INS_THREADS = 256;
+
+template <int NW, class Sink>
+__device__ __forceinline__ void chop_read(const KParams<NW>& kp, const u64* __restrict__ wp, int L, Sink& sink) {
+    const int K = kp.K;
+    Kmer<NW> fwd = kzero<NW>(), rc = kzero<NW>();
+    u64 cur = wp[0];
+    unsigned c = (unsigned)(cur & 3);          // base i
+    for (int i = 0; i < L; i++) {
+        // look ahead one base (needed as the right neighbour of the k-mer ending at i)
+        unsigned cn = 4;
+        if (i + 1 < L) {
+            if (((i + 1) & 31) == 0) cur = wp[(i + 1) >> 5];
+            cn = (unsigned)((cur >> (2 * ((i + 1) & 31))) & 3);
+        }
+        unsigned dropped = kfirst(fwd, kp);    // base j-1 (valid when j >= 1)
+        fwd = knext(fwd, c, kp);
+        rc = kprev(rc, c ^ 2u, kp);
+        int j = i - K + 1;
+        if (j >= 0) {
+            unsigned pv = j > 0 ? dropped : 4u;
+            bool sm = kless(fwd, rc);          // KmerSmaller(word, bal_word); tie -> rc branch
+            unsigned left = sm ? pv : (cn < 4 ? (cn ^ 2u) : 4u);
+            unsigned right = sm ? cn : (pv < 4 ? (pv ^ 2u) : 4u);
+            sink(sm ? fwd : rc, left, right, j);
+        }
+        c = cn;
+    }
+}
+
 template <int NW>
-__global__ void __launch_bounds__(256) k_chop_insert(Table<NW> tab, KParams<NW> kp, const u64* __restrict__ words,
-                                                     const u32* __restrict__ lens, u64 n_rec, int W64, u64 ord_base, u64 ord_stride,
-                                                     int world, int myrank, u64* counters) {
+struct InsertSink {
+    const Table<NW>& tab;
+    u64 rank_base;
+    unsigned& my_new;
+    __device__ __forceinline__ void operator()(const Kmer<NW>& canon, unsigned left, unsigned right, int j) {
+        my_new += table_insert(tab, canon, left, right, rank_base | (u64)j);
+    }
+};
+
+template <int NW>
+__global__ void __launch_bounds__(INS_THREADS) k_chop_insert(Table<NW> tab, KParams<NW> kp, const u64* __restrict__ words,
+                                                             const u32* __restrict__ lens, u64 n_rec, int W64, u64 ord_base, u64 ord_stride,
+                                                             u64* counters) {
     __shared__ unsigned s_new;
     if (threadIdx.x == 0) s_new = 0;
     __syncthreads();
-    const int K = kp.K;
     unsigned my_new = 0;
     for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += (u64)gridDim.x * blockDim.x) {
         const int L = (int)lens[r];
-        if (L < K + 1) continue;
-        const u64* wp = words + r * (u64)W64;
-        const u64 rank_base = (ord_base + r * ord_stride) << 16;
-        Kmer<NW> fwd = kzero<NW>(), rc = kzero<NW>();
-        u64 cur = wp[0];
-        unsigned c = (unsigned)(cur & 3);          // base i
-        for (int i = 0; i < L; i++) {
-            // look ahead one base (needed as the right neighbour of the k-mer ending at i)
-            unsigned cn = 4;
-            if (i + 1 < L) {
-                if (((i + 1) & 31) == 0) cur = wp[(i + 1) >> 5];
-                cn = (unsigned)((cur >> (2 * ((i + 1) & 31))) & 3);
-            }
-            unsigned dropped = kfirst(fwd, kp);    // base j-1 (valid when j >= 1)
-            fwd = knext(fwd, c, kp);
-            rc = kprev(rc, c ^ 2u, kp);
-            int j = i - K + 1;
-            if (j >= 0) {
-                unsigned pv = j > 0 ? dropped : 4u;
-                bool sm = kless(fwd, rc);          // KmerSmaller(word, bal_word); tie -> rc branch
-                Kmer<NW> canon = sm ? fwd : rc;
-                unsigned left = sm ? pv : (cn < 4 ? (cn ^ 2u) : 4u);
-                unsigned right = sm ? cn : (pv < 4 ? (pv ^ 2u) : 4u);
-                if (world > 1 && (int)(mix64(table_hash(canon) ^ 0x5bd1e995ull) % (u64)world) != myrank) { c = cn; continue; }
-                bool claimed;
-                u64 idx = table_find_or_claim(tab, canon, &claimed);
-                my_new += claimed;
-                slot_apply(tab.slots + idx, left, right, rank_base | (u64)j);
-            }
-            c = cn;
-        }
+        if (L < kp.K + 1) continue;
+        InsertSink<NW> sink{tab, (ord_base + r * ord_stride) << 16, my_new};
+        chop_read(kp, words + r * (u64)W64, L, sink);
     }
     if (my_new) atomicAdd(&s_new, my_new);
     __syncthreads();
@@ -262,9 +277,12 @@ void EngineT<NW>::ensure_table(u64 incoming) {
 }
 
 // ------------------------------------------------------------------------------------------------ feed_text
+static double host_now() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; }
+
 template <int NW>
 void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int fastq, uint64_t ord_base, uint64_t ord_stride,
                             int reverse_seq, int maxlen) {
+    double t_a = host_now(), t_b = 0, t_c = 0, t_d = 0, t_e = 0;
     last_records_ = 0;
     if (nbytes == 0) return;
     PG_CUDA(cudaSetDevice(prm_.device));
@@ -296,6 +314,7 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     if ((n_lines + (open_tail ? 1 : 0)) % lpr != 0)
         throw std::runtime_error("pgb200: text chunk does not hold whole FASTA/FASTQ records (line count not a multiple of 2/4)");
     if (n_rec == 0) return;
+    t_b = host_now();
     line_buf_.ensure(2 * n_rec * sizeof(u64));
     u64* seq_start = line_buf_.template as<u64>();
     u64* seq_end = seq_start + n_rec;
@@ -317,6 +336,7 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     PG_CUDA(cudaMalloc(&ch.words, n_rec * (u64)W64_ * sizeof(u64)));
     PG_CUDA(cudaMalloc(&ch.len, n_rec * sizeof(u32)));
     chunks_.push_back(ch);
+    t_c = host_now();
     {
         u64 warps = n_rec;
         unsigned blocks = (unsigned)std::min<u64>((warps + 7) / 8, 148ull * 64);
@@ -330,21 +350,27 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     ensure_table(0);   // creates the table on first use, refreshes h_cnt_ (decode is complete after this sync)
     u64 chunk_inst = h_cnt_[C_INSTANCES] - before_inst;
     ensure_table(chunk_inst);
+    t_d = host_now();
+    if (l2gran_mode_ == 2) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     PG_CUDA(cudaEventRecord(ev_[2], st_));
     {
-        unsigned blocks = (unsigned)std::min<u64>((n_rec + 255) / 256, 148ull * 32);
-        k_chop_insert<NW><<<blocks, 256, 0, st_>>>(tab_, kp_, ch.words, ch.len, n_rec, W64_, ord_base, ord_stride, prm_.world, prm_.rank,
-                                                   d_cnt_);
+        unsigned blocks = (unsigned)std::min<u64>((n_rec + INS_THREADS - 1) / INS_THREADS, 148ull * 64);
+        k_chop_insert<NW><<<blocks, INS_THREADS, 0, st_>>>(tab_, kp_, ch.words, ch.len, n_rec, W64_, ord_base, ord_stride, d_cnt_);
         PG_CUDA(cudaGetLastError());
     }
     PG_CUDA(cudaEventRecord(ev_[3], st_));
     sync();
+    if (l2gran_mode_ == 2) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 128);
     float ms;
     PG_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1])); p1_.ms_decode += ms;
     PG_CUDA(cudaEventElapsedTime(&ms, ev_[2], ev_[3])); p1_.ms_insert += ms;
     p1_.launches += 8;
     last_records_ = n_rec;
     total_records_ += n_rec;
+    t_e = host_now();
+    if (prm_.verbose >= 2)
+        fprintf(stderr, "[pgb200] chunk %zu: %llu rec, host ms: count %.2f alloc %.2f decode+table %.2f insert %.2f (gpu: decode %.2f insert %.2f)\n", chunks_.size(),
+                (unsigned long long)n_rec, t_b - t_a, t_c - t_b, t_d - t_c, t_e - t_d, p1_.ms_decode, p1_.ms_insert);
 }
 
 template <int NW>
@@ -431,6 +457,10 @@ void EngineT<NW>::sweeps(SweepStats* st) {
 template <int NW>
 EngineT<NW>::EngineT(const PgParams& p) : prm_(p) {
     PG_CUDA(cudaSetDevice(p.device));
+    // Random 32 B slot accesses: do not let L2 promote a sector miss to a 64/128 B DRAM fetch (measured with ncu: 259 B of
+    // DRAM reads per k-mer instance with the default granularity, profiles/r01_insert_ncu.md)
+    if (const char* g = getenv("PGB200_L2GRAN")) l2gran_mode_ = atoi(g);
+    if (l2gran_mode_ == 1) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     kp_ = make_kparams<NW>(p.K);
     PG_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     for (auto& e : ev_) PG_CUDA(cudaEventCreate(&e));

@@ -92,12 +92,21 @@ struct Table {
 // (observed: the publish-wait below was turned into a single load, producing duplicate 256-bit keys on the GPU).
 PG_D U128 ldcg128(const void* p) {
     U128 r;
-    asm volatile("ld.relaxed.gpu.global.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(r.a), "=l"(r.b) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(r.a), "=l"(r.b) : "l"(p) : "memory");
+    return r;
+}
+struct alignas(32) U256 {
+    u64 a, b, c, d;
+};
+// one 32-byte sector in one request (LDG.E.256 on sm_100a): key + payload + aux of a K<=63 slot
+PG_D U256 ld256(const void* p) {
+    U256 r;
+    asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p) : "memory");
     return r;
 }
 PG_D u64 ldcg64(const void* p) {
     u64 r;
-    asm volatile("ld.relaxed.gpu.global.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");
     return r;
 }
 PG_D u64 ldacq64(const void* p) {
@@ -193,6 +202,47 @@ PG_D void slot_apply(Slot<NW>* s, unsigned left, unsigned right, u64 rank) {
         if (old.a == cur.a && old.b == cur.b) return;
         cur = old;
     }
+}
+
+// Fused find-or-claim + apply for one k-mer instance.  Returns true if this call inserted the key.
+template <int NW>
+PG_D bool table_insert(const Table<NW>& t, const Kmer<NW>& k, unsigned left, unsigned right, u64 rank) {
+    bool claimed;
+    u64 idx = table_find_or_claim(t, k, &claimed);
+    slot_apply(t.slots + idx, left, right, rank);
+    return claimed;
+}
+// K <= 63: the whole 32 B slot arrives with ONE 256-bit load per probe, so a hit needs no second read before the CAS and
+// a fresh claim knows the {payload, rank} it will find (the memset state).
+template <>
+PG_D bool table_insert<2>(const Table<2>& t, const Kmer<2>& k, unsigned left, unsigned right, u64 rank) {
+    u64 idx = table_hash(k) & t.mask;
+    bool claimed = false;
+    U128 cur;
+    Slot<2>* s;
+    for (;;) {
+        s = t.slots + idx;
+        U256 v = ld256(s);
+        if (v.a == k.w[0] && v.b == k.w[1]) { cur.a = v.c; cur.b = v.d; break; }
+        if (v.a == EMPTY64 && v.b == EMPTY64) {
+            U128 want{k.w[0], k.w[1]}, empty{EMPTY64, EMPTY64};
+            U128 old = atomicCAS(reinterpret_cast<U128*>(s->key), empty, want);
+            if (old.a == EMPTY64 && old.b == EMPTY64) { claimed = true; cur.a = PAYLOAD_FRESH; cur.b = EMPTY64; break; }
+            if (old.a == k.w[0] && old.b == k.w[1]) { cur = ldcg128(&s->payload); break; }
+        }
+        idx = (idx + 1) & t.mask;
+    }
+    U128* pr = reinterpret_cast<U128*>(&s->payload);
+    for (;;) {
+        U128 nxt;
+        nxt.a = payload_apply(cur.a, left, right);
+        nxt.b = rank < cur.b ? rank : cur.b;
+        if (nxt.a == cur.a && nxt.b == cur.b) break;
+        U128 old = atomicCAS(pr, cur, nxt);
+        if (old.a == cur.a && old.b == cur.b) break;
+        cur = old;
+    }
+    return claimed;
 }
 
 template <int NW>

@@ -91,3 +91,21 @@ def test_downstream_contig_consumes_gpu_output(tmp_path):
     for pre in (ref, gpu):
         util.run([util.REF63, "contig", "-g", pre, "-R"])
     util.compare(ref, gpu, ["contig", "Arc", "updated.edge", "ContigIndex"])
+
+
+def test_midsize_pe_k63_vs_reference(tmp_path):
+    """2 Mbp genome, 30x, 150 bp PE FASTQ, K=63, -p 8 -a 2 -R (17.6 M k-mer instances): exercises many tip rounds, long edges."""
+    import numpy as np
+    g = synth.genome(2_000_000, 11, repeat=(2000, 4))
+    r1, r2 = synth.pe_reads(g, 200_000, 150, 300, 0.001, 12)
+    d = str(tmp_path)
+    synth.write_fastq(os.path.join(d, "a_1.fq"), r1, "m")
+    synth.write_fastq(os.path.join(d, "a_2.fq"), r2, "m")
+    cfg = os.path.join(d, "mid.cfg")
+    synth.write_config(cfg, 150, [{"avg_ins": 300, "files": [("q1", os.path.join(d, "a_1.fq")), ("q2", os.path.join(d, "a_2.fq"))]}])
+    ref, gpu = str(tmp_path / "ref"), str(tmp_path / "gpu")
+    lr = _oracle(0, cfg, ref, 63, 8, ("-a", "2", "-R"))
+    lg = _engine(0, cfg, gpu, 63, 8, ("-a", "2", "-R"))
+    util.compare(ref, gpu, util.SUFFIXES_R)
+    if util.have_ref():
+        assert _counter_lines(lr) == _counter_lines(lg)
