@@ -71,6 +71,15 @@ void pgb200_host_free(void *p);
 int pgb200_feed_text(pgb200_engine *e, const char *text, size_t nbytes, int on_device, int fastq, uint64_t ord_base,
                      uint64_t ord_stride, int reverse_seq, int maxlen);
 uint64_t pgb200_last_chunk_records(pgb200_engine *e);
+
+/* Multi-GPU (params.world > 1): the k-mer space is sharded by an owner hash.  pgb200_feed_text then only decodes the chunk and
+ * groups its (k-mer, links, rank) tuples by owner rank in a device buffer; the caller moves range o to rank o (one bucketed
+ * all-to-all per round, e.g. NCCL via torch.distributed.all_to_all_single) and hands what it received to pgb200_apply_tuples.
+ * This replaces the reference's "every thread scans the whole batch and keeps hash % thrd_num == id" (prlHashReads.c:79-90).
+ * ranges has world+1 entries (tuple indices); a tuple is tuple_bytes bytes (32 for K <= 63, 64 for K <= 127).            */
+const void *pgb200_exchange_buffer(pgb200_engine *e, uint64_t *ranges, int *tuple_bytes);
+int pgb200_exchange_clear(pgb200_engine *e);
+int pgb200_apply_tuples(pgb200_engine *e, const void *dev_tuples, uint64_t n_tuples);
 int pgb200_finish_pass1(pgb200_engine *e, pgb200_pass1_stats *st);
 int pgb200_reset_pass1(pgb200_engine *e);
 /* delow (-d) + mark linear + coverage histogram: hist[c] = number of k-mers with coverage c (the .kmerFreq lines are hist[1..255]) */

@@ -15,7 +15,7 @@ BIN127 = os.path.join(_HERE, "bin", "pregraph-b200-127mer")
 
 EXPORTS = [
     "pgb200_last_error", "pgb200_default_params", "pgb200_create", "pgb200_destroy", "pgb200_host_alloc", "pgb200_host_free",
-    "pgb200_feed_text", "pgb200_last_chunk_records", "pgb200_finish_pass1", "pgb200_reset_pass1", "pgb200_sweeps",
+    "pgb200_feed_text", "pgb200_last_chunk_records", "pgb200_exchange_buffer", "pgb200_exchange_clear", "pgb200_apply_tuples", "pgb200_finish_pass1", "pgb200_reset_pass1", "pgb200_sweeps",
     "pgb200_build_layout", "pgb200_node_count", "pgb200_dump_nodes", "pgb200_remove_tips", "pgb200_kmer2edges",
     "pgb200_read2edge", "pgb200_output_vertex", "pgb200_pregraph_main", "call_pregraph",
 ]
@@ -57,6 +57,10 @@ def load():
     lib.pgb200_feed_text.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int]
     lib.pgb200_last_chunk_records.restype = C.c_uint64
     lib.pgb200_last_chunk_records.argtypes = [C.c_void_p]
+    lib.pgb200_exchange_buffer.restype = C.c_void_p
+    lib.pgb200_exchange_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+    lib.pgb200_exchange_clear.argtypes = [C.c_void_p]
+    lib.pgb200_apply_tuples.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     lib.pgb200_finish_pass1.argtypes = [C.c_void_p, C.POINTER(Pass1Stats)]
     lib.pgb200_reset_pass1.argtypes = [C.c_void_p]
     lib.pgb200_sweeps.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -115,6 +119,20 @@ class PregraphEngine:
         self._ck(self.lib.pgb200_feed_text(self.h, ptr, n, int(on_device), int(fastq), ord_base, ord_stride, reverse_seq,
                                            maxlen if maxlen is not None else self.params.max_rd_len))
         return self.lib.pgb200_last_chunk_records(self.h)
+
+    def exchange_buffer(self):
+        """-> (device pointer, [world+1] tuple range starts, bytes per tuple) of the owner-grouped tuples of the last fed chunk."""
+        w = max(1, self.params.world)
+        ranges = (C.c_uint64 * (w + 1))()
+        tb = C.c_int()
+        ptr = self.lib.pgb200_exchange_buffer(self.h, ranges, C.byref(tb))
+        return ptr or 0, list(ranges), tb.value
+
+    def exchange_clear(self):
+        self._ck(self.lib.pgb200_exchange_clear(self.h))
+
+    def apply_tuples(self, dev_ptr, n_tuples):
+        self._ck(self.lib.pgb200_apply_tuples(self.h, C.c_void_p(int(dev_ptr)), n_tuples))
 
     def finish_pass1(self) -> Pass1Stats:
         st = Pass1Stats()

@@ -1,0 +1,207 @@
+// bucket.cu -- locality + ownership for the insert: instead of letting 3e5 threads hit random HBM sectors all over a
+// 17 GB table, the (k-mer, links, rank) tuples of a chunk are first grouped by (owner GPU, table region) and then
+// applied region by region, so that a region's slots (8-16 MB) stay L2-resident while its tuples stream through.
+// The same grouping IS the multi-GPU exchange format: owner-major ranges of the tuple buffer are what the bucketed
+// NCCL all-to-all ships (the reference's analogue is "every thread scans the batch and keeps
+// hash % thrd_num == id", prlHashReads.c:79-90).
+//
+// Exact counting sort, no global atomics: K_count writes per-(tile, bucket) counts, one scan in bucket-major order turns
+// them into offsets, K_scatter re-chops the tile and places each tuple with a shared-memory cursor.  A tile is the 256
+// reads of one block.  DRAM traffic per k-mer instance: 8*(NW+1) B written + read (streaming) instead of a 128 B random
+// line fetch + 32 B write-back.
+#include "engine_impl.cuh"
+#include "scan.cuh"
+#include "chop.cuh"
+
+namespace pgb {
+
+constexpr int BK_THREADS = 256;
+// tuple = key words + meta, padded to whole 32 B sectors so that a tuple is written with full-sector stores (no RMW fills)
+template <int NW> struct TupleW { static constexpr int value = NW == 2 ? 4 : 8; };
+
+template <int NW>
+__device__ __forceinline__ unsigned bucket_of(const Kmer<NW>& k, u64 mask, int region_shift, int region_bits, int world) {
+    u64 h = table_hash(k);
+    unsigned region = region_bits ? (unsigned)((h & mask) >> region_shift) : 0u;
+    unsigned owner = world > 1 ? (unsigned)((h >> 40) % (u64)world) : 0u;
+    return (owner << region_bits) | region;
+}
+
+template <int NW>
+struct CountSink {
+    unsigned* hist;
+    u64 mask;
+    int region_shift, region_bits, world;
+    __device__ __forceinline__ void operator()(const Kmer<NW>& canon, unsigned, unsigned, int) {
+        atomicAdd(&hist[bucket_of(canon, mask, region_shift, region_bits, world)], 1u);
+    }
+};
+
+template <int NW>
+__global__ void __launch_bounds__(BK_THREADS) k_bucket_count(KParams<NW> kp, const u64* __restrict__ words, const u32* __restrict__ lens, u64 n_rec,
+                                                              int W64, u64 mask, int region_shift, int region_bits, int world, int NB, u32* tilecnt) {
+    extern __shared__ unsigned s_hist[];
+    for (int b = threadIdx.x; b < NB; b += BK_THREADS) s_hist[b] = 0;
+    __syncthreads();
+    u64 r = (u64)blockIdx.x * BK_THREADS + threadIdx.x;
+    if (r < n_rec) {
+        int L = (int)lens[r];
+        if (L >= kp.K + 1) {
+            CountSink<NW> sink{s_hist, mask, region_shift, region_bits, world};
+            chop_read(kp, words + r * (u64)W64, L, sink);
+        }
+    }
+    __syncthreads();
+    u32* row = tilecnt + (u64)blockIdx.x * NB;
+    for (int b = threadIdx.x; b < NB; b += BK_THREADS) row[b] = s_hist[b];
+}
+
+// bucket-major exclusive scan over the (tile x bucket) count matrix
+struct TileCntIn {
+    const u32* cnt;
+    u64 n_tiles;
+    int NB;
+    __device__ u64 operator()(u64 i) const { u64 b = i / n_tiles, t = i - b * n_tiles; return cnt[t * NB + b]; }
+};
+struct TileOffOut {
+    u32* off;
+    u64 n_tiles;
+    int NB;
+    __device__ void operator()(u64 i, u64 prefix, u64) const { u64 b = i / n_tiles, t = i - b * n_tiles; off[t * NB + b] = (u32)prefix; }
+};
+
+template <int NW>
+struct ScatterSink {
+    unsigned* cursor;
+    u64* tuples;
+    u64 ord;
+    u64 mask;
+    int region_shift, region_bits, world;
+    __device__ __forceinline__ void operator()(const Kmer<NW>& canon, unsigned left, unsigned right, int j) {
+        unsigned b = bucket_of(canon, mask, region_shift, region_bits, world);
+        u64 p = atomicAdd(&cursor[b], 1u);
+        u64* t = tuples + p * TupleW<NW>::value;
+        u64 m = tuple_meta(ord, j, left, right);
+        if (NW == 2) {
+            asm volatile("st.global.cs.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(t), "l"(canon.w[0]), "l"(canon.w[1]), "l"(m), "l"(0ull) : "memory");
+        } else {
+            asm volatile("st.global.cs.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(t), "l"(canon.w[0]), "l"(canon.w[1]), "l"(canon.w[2]), "l"(canon.w[NW - 1]) : "memory");
+            asm volatile("st.global.cs.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(t + 4), "l"(m), "l"(0ull), "l"(0ull), "l"(0ull) : "memory");
+        }
+    }
+};
+
+template <int NW>
+__global__ void __launch_bounds__(BK_THREADS) k_bucket_scatter(KParams<NW> kp, const u64* __restrict__ words, const u32* __restrict__ lens, u64 n_rec,
+                                                                int W64, u64 ord_base, u64 ord_stride, u64 mask, int region_shift, int region_bits,
+                                                                int world, int NB, const u32* tileoff, u64* tuples) {
+    extern __shared__ unsigned s_cur[];
+    const u32* row = tileoff + (u64)blockIdx.x * NB;
+    for (int b = threadIdx.x; b < NB; b += BK_THREADS) s_cur[b] = row[b];
+    __syncthreads();
+    u64 r = (u64)blockIdx.x * BK_THREADS + threadIdx.x;
+    if (r < n_rec) {
+        int L = (int)lens[r];
+        if (L >= kp.K + 1) {
+            ScatterSink<NW> sink{s_cur, tuples, ord_base + r * ord_stride, mask, region_shift, region_bits, world};
+            chop_read(kp, words + r * (u64)W64, L, sink);
+        }
+    }
+}
+
+// streaming read of the tuple (evict-first: it is touched exactly once and must not push table lines out of L2)
+__device__ __forceinline__ u64 ld_stream(const u64* p) {
+    u64 v;
+    asm volatile("ld.global.cs.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(BK_THREADS) k_apply_tuples(Table<NW> tab, const u64* __restrict__ tuples, u64 n, u64* counters) {
+    __shared__ unsigned s_new;
+    if (threadIdx.x == 0) s_new = 0;
+    __syncthreads();
+    unsigned my_new = 0;
+    // NOT a grid-stride loop: one tuple per thread and as many blocks as needed.  The hardware hands out blocks in index
+    // order, so the blocks resident at any moment cover one contiguous window of the region-sorted tuples (a persistent
+    // grid drifts apart and the window -- hence the table working set -- grows without bound; measured: 180 B of DRAM reads
+    // per tuple with the persistent variant).
+    u64 i = (u64)blockIdx.x * BK_THREADS + threadIdx.x;
+    if (i < n) {
+        const u64* t = tuples + i * TupleW<NW>::value;
+        U256 a;
+        asm volatile("ld.global.cs.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a.a), "=l"(a.b), "=l"(a.c), "=l"(a.d) : "l"(t));
+        Kmer<NW> k;
+        u64 m;
+        if (NW == 2) { k.w[0] = a.a; k.w[NW - 1] = a.b; m = a.c; }
+        else { k.w[0] = a.a; k.w[1] = a.b; k.w[NW == 4 ? 2 : 0] = a.c; k.w[NW - 1] = a.d; m = ld_stream(t + 4); }
+        my_new += table_insert(tab, k, (unsigned)((m >> 3) & 7), (unsigned)(m & 7), m >> 6);
+    }
+    if (my_new) atomicAdd(&s_new, my_new);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_new) atomicAdd(&counters[C_DISTINCT], (u64)s_new);
+}
+
+template <int NW>
+void EngineT<NW>::bucket_chunk(const ReadChunk& ch) {
+    const int world = prm_.world > 1 ? prm_.world : 1;
+    // regions of ~8 MB of table (capped so that the per-block histogram fits in shared memory)
+    int log2cap = 0;
+    while ((1ull << log2cap) < cap_) log2cap++;
+    u64 table_bytes = cap_ * sizeof(Slot<NW>);
+    int rb = 0;
+    while ((table_bytes >> rb) > (8ull << 20) && rb < 12 && world * (2 << rb) <= 8192) rb++;
+    if (rb > log2cap) rb = log2cap;
+    region_bits_ = rb;
+    const int region_shift = log2cap - rb;
+    const int NB = world << rb;
+    n_buckets_ = NB;
+    const u64 n_tiles = (ch.n_rec + BK_THREADS - 1) / BK_THREADS;
+    const u64 cells = n_tiles * (u64)NB;
+    tilecnt_buf_.ensure(cells * sizeof(u32));
+    tileoff_buf_.ensure(cells * sizeof(u32));
+    scan_buf_.ensure(scan_scratch_elems(cells) * sizeof(u64));
+    size_t smem = (size_t)NB * sizeof(unsigned);
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+        cudaFuncSetAttribute(k_bucket_count<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(k_bucket_scatter<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr_set = true;
+    }
+    k_bucket_count<NW><<<(unsigned)n_tiles, BK_THREADS, smem, st_>>>(kp_, ch.words, ch.len, ch.n_rec, W64_, tab_.mask, region_shift, rb, world, NB,
+                                                                     tilecnt_buf_.template as<u32>());
+    PG_CUDA(cudaGetLastError());
+    device_scan(TileCntIn{tilecnt_buf_.template as<u32>(), n_tiles, NB}, TileOffOut{tileoff_buf_.template as<u32>(), n_tiles, NB}, cells,
+                scan_buf_.template as<u64>(), d_cnt_ + C_MISC1, st_);
+    // total + owner range starts (tile 0's offset of an owner's first bucket == start of that owner's range)
+    std::vector<u32> first_row(NB);
+    PG_CUDA(cudaMemcpyAsync(first_row.data(), tileoff_buf_.p, NB * sizeof(u32), cudaMemcpyDeviceToHost, st_));
+    read_counters();
+    n_tuples_ = h_cnt_[C_MISC1];
+    if (n_tuples_ >= 0xFFFFFFFFull) throw std::runtime_error("pgb200: more than 2^32 k-mer instances in one chunk; feed smaller chunks");
+    owner_start_.assign(world + 1, n_tuples_);
+    for (int o = 0; o < world; o++) owner_start_[o] = first_row[(size_t)o << rb];
+    tuple_buf_.ensure((n_tuples_ + 1) * TupleW<NW>::value * sizeof(u64));
+    k_bucket_scatter<NW><<<(unsigned)n_tiles, BK_THREADS, smem, st_>>>(kp_, ch.words, ch.len, ch.n_rec, W64_, ch.ord_base, ch.ord_stride, tab_.mask,
+                                                                       region_shift, rb, world, NB, tileoff_buf_.template as<u32>(),
+                                                                       tuple_buf_.template as<u64>());
+    PG_CUDA(cudaGetLastError());
+    p1_.launches += 5;
+}
+
+template <int NW>
+void EngineT<NW>::apply_tuples(const u64* tuples, u64 n) {
+    if (!n) return;
+    if (!tab_.slots) ensure_table(n);
+    unsigned blocks = (unsigned)((n + BK_THREADS - 1) / BK_THREADS);
+    k_apply_tuples<NW><<<blocks, BK_THREADS, 0, st_>>>(tab_, tuples, n, d_cnt_);
+    PG_CUDA(cudaGetLastError());
+    p1_.launches += 1;
+}
+
+template void EngineT<2>::bucket_chunk(const ReadChunk&);
+template void EngineT<4>::bucket_chunk(const ReadChunk&);
+template void EngineT<2>::apply_tuples(const u64*, u64);
+template void EngineT<4>::apply_tuples(const u64*, u64);
+
+}   // namespace pgb

@@ -67,6 +67,11 @@ public:
     virtual void feed_text(const char* text, size_t nbytes, bool on_device, int fastq, uint64_t ord_base, uint64_t ord_stride,
                            int reverse_seq, int maxlen) = 0;
     virtual uint64_t last_chunk_records() const = 0;
+    // multi-GPU (world > 1): after feed_text the chunk's tuples sit in an exchange buffer grouped by owner rank.
+    // ranges[o]..ranges[o+1] (in tuples) belong to owner o; tuple_bytes per tuple.  apply_received() inserts tuples this rank owns.
+    virtual const void* exchange_buffer(uint64_t* ranges /*world+1*/, int* tuple_bytes) = 0;
+    virtual void exchange_clear() = 0;
+    virtual void apply_received(const void* dev_tuples, uint64_t n) = 0;
     virtual void finish_pass1(Pass1Stats* st) = 0;
     virtual void reset_pass1() = 0;   // drop reads + table (bench: repeat the step)
     virtual void sweeps(SweepStats* st) = 0;            // delow + mark linear + kmerFreq histogram

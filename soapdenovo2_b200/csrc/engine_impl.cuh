@@ -105,6 +105,38 @@ public:
     DevBuf patch_buf_;          // (K+1)-mer patch table
     u64 patch_mask_ = 0;
 
+    // bucketed insert path (bucket.cu): tuples {key words, meta} grouped by (owner GPU, table region)
+    int bucket_mode_ = 0;       // PGB200_BUCKET=1: single-GPU inserts also go through the bucketed (region-sorted) path
+    DevBuf tuple_buf_, tilecnt_buf_, tileoff_buf_;
+    u64 n_tuples_ = 0;          // tuples currently in tuple_buf_
+    int n_buckets_ = 0, region_bits_ = 0;
+    std::vector<u64> owner_start_;   // [world + 1] tuple offsets of each owner's range in tuple_buf_
+    void bucket_chunk(const ReadChunk& ch);
+    void apply_tuples(const u64* tuples, u64 n);
+public:
+    // multi-GPU exchange surface (C-ABI: pgb200_exchange_*)
+    static constexpr int tuple_words() { return NW == 2 ? 4 : 8; }
+    const void* exchange_buffer(uint64_t* ranges, int* tuple_bytes) override {
+        const int world = prm_.world > 1 ? prm_.world : 1;
+        for (int o = 0; o <= world; o++) ranges[o] = owner_start_.size() == (size_t)world + 1 ? owner_start_[o] : 0;
+        *tuple_bytes = tuple_words() * 8;
+        sync();
+        return tuple_buf_.p;
+    }
+    void exchange_clear() override { owner_start_.clear(); n_tuples_ = 0; }
+    void apply_received(const void* tuples, uint64_t n) override {
+        if (!n) return;
+        ensure_table(0);
+        ensure_table(n);
+        PG_CUDA(cudaEventRecord(ev_[2], st_));
+        apply_tuples(reinterpret_cast<const u64*>(tuples), n);
+        PG_CUDA(cudaEventRecord(ev_[3], st_));
+        sync();
+        float ms;
+        PG_CUDA(cudaEventElapsedTime(&ms, ev_[2], ev_[3]));
+        p1_.ms_insert += ms;
+    }
+
     // helpers
     void ensure_table(u64 need_free);
     void grow_table(u64 new_cap);

@@ -85,6 +85,11 @@ extern "C" int pgb200_feed_text(pgb200_engine* e, const char* text, size_t nbyte
     PG_TRY e->e->feed_text(text, nbytes, on_device != 0, fastq, ord_base, ord_stride, reverse_seq, maxlen); PG_CATCH
 }
 extern "C" uint64_t pgb200_last_chunk_records(pgb200_engine* e) { return e->e->last_chunk_records(); }
+extern "C" const void* pgb200_exchange_buffer(pgb200_engine* e, uint64_t* ranges, int* tuple_bytes) {
+    try { return e->e->exchange_buffer(ranges, tuple_bytes); } catch (const std::exception& ex) { g_err = ex.what(); return nullptr; }
+}
+extern "C" int pgb200_exchange_clear(pgb200_engine* e) { PG_TRY e->e->exchange_clear(); PG_CATCH }
+extern "C" int pgb200_apply_tuples(pgb200_engine* e, const void* dev_tuples, uint64_t n) { PG_TRY e->e->apply_received(dev_tuples, n); PG_CATCH }
 extern "C" int pgb200_finish_pass1(pgb200_engine* e, pgb200_pass1_stats* st) {
     PG_TRY
     Pass1Stats s;

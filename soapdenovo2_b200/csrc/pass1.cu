@@ -11,6 +11,7 @@
 // order and is evaluated once per DISTINCT k-mer in layout.cu.
 #include "engine_impl.cuh"
 #include "scan.cuh"
+#include "chop.cuh"
 #include <ctime>
 
 namespace pgb {
@@ -147,34 +148,6 @@ __global__ void __launch_bounds__(256) k_decode_pack(const unsigned char* __rest
 //  memory ring -- was measured and dropped: 38.6 ms vs 28.0 ms per 5.3e8 instances at every distance; the kernel is bound
 //  by the random-sector rate of L2/HBM, not by exposed latency.  profiles/r01_insert_ncu.md.)
 constexpr int INS_THREADS = 256;
-
-template <int NW, class Sink>
-__device__ __forceinline__ void chop_read(const KParams<NW>& kp, const u64* __restrict__ wp, int L, Sink& sink) {
-    const int K = kp.K;
-    Kmer<NW> fwd = kzero<NW>(), rc = kzero<NW>();
-    u64 cur = wp[0];
-    unsigned c = (unsigned)(cur & 3);          // base i
-    for (int i = 0; i < L; i++) {
-        // look ahead one base (needed as the right neighbour of the k-mer ending at i)
-        unsigned cn = 4;
-        if (i + 1 < L) {
-            if (((i + 1) & 31) == 0) cur = wp[(i + 1) >> 5];
-            cn = (unsigned)((cur >> (2 * ((i + 1) & 31))) & 3);
-        }
-        unsigned dropped = kfirst(fwd, kp);    // base j-1 (valid when j >= 1)
-        fwd = knext(fwd, c, kp);
-        rc = kprev(rc, c ^ 2u, kp);
-        int j = i - K + 1;
-        if (j >= 0) {
-            unsigned pv = j > 0 ? dropped : 4u;
-            bool sm = kless(fwd, rc);          // KmerSmaller(word, bal_word); tie -> rc branch
-            unsigned left = sm ? pv : (cn < 4 ? (cn ^ 2u) : 4u);
-            unsigned right = sm ? cn : (pv < 4 ? (pv ^ 2u) : 4u);
-            sink(sm ? fwd : rc, left, right, j);
-        }
-        c = cn;
-    }
-}
 
 template <int NW>
 struct InsertSink {
@@ -353,7 +326,12 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     t_d = host_now();
     if (l2gran_mode_ == 2) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     PG_CUDA(cudaEventRecord(ev_[2], st_));
-    {
+    if (prm_.world > 1) {
+        bucket_chunk(ch);                       // tuples stay in the exchange buffer: caller runs the all-to-all
+    } else if (bucket_mode_) {
+        bucket_chunk(ch);
+        apply_tuples(tuple_buf_.template as<u64>(), n_tuples_);
+    } else {
         unsigned blocks = (unsigned)std::min<u64>((n_rec + INS_THREADS - 1) / INS_THREADS, 148ull * 64);
         k_chop_insert<NW><<<blocks, INS_THREADS, 0, st_>>>(tab_, kp_, ch.words, ch.len, n_rec, W64_, ord_base, ord_stride, d_cnt_);
         PG_CUDA(cudaGetLastError());
@@ -460,6 +438,7 @@ EngineT<NW>::EngineT(const PgParams& p) : prm_(p) {
     // Random 32 B slot accesses: do not let L2 promote a sector miss to a 64/128 B DRAM fetch (measured with ncu: 259 B of
     // DRAM reads per k-mer instance with the default granularity, profiles/r01_insert_ncu.md)
     if (const char* g = getenv("PGB200_L2GRAN")) l2gran_mode_ = atoi(g);
+    if (const char* g = getenv("PGB200_BUCKET")) bucket_mode_ = atoi(g);
     if (l2gran_mode_ == 1) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     kp_ = make_kparams<NW>(p.K);
     PG_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));

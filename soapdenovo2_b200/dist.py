@@ -1,0 +1,48 @@
+"""Multi-GPU plumbing for pass 1: the bucketed all-to-all of (k-mer, links, rank) tuples between owner ranks.
+
+torch.distributed (NCCL over NVLink on the GPUs, gloo in the CPU tests) is only the transport; the tuples are produced by
+k_bucket_scatter and consumed by k_apply_tuples inside libpregraph_b200.so (include/pregraph_b200.h, pgb200_exchange_buffer /
+pgb200_apply_tuples).  One round = every rank has fed (at most) one chunk; rank r then receives every tuple whose owner
+hash maps to r.  This is the exchange step SURVEY.md 8(e) describes; the reference's analogue is the per-thread owner filter
+`hash % thrd_num == id` over a shared batch (prlHashReads.c:79-90).
+"""
+from __future__ import annotations
+
+
+class DeviceMemory:
+    """Expose a raw device pointer to torch (zero-copy) through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def split_sizes(ranges, tuple_bytes):
+    """[world+1] tuple range starts -> per-owner byte counts."""
+    return [(ranges[o + 1] - ranges[o]) * tuple_bytes for o in range(len(ranges) - 1)]
+
+
+def all_to_all_bytes(torch, dist, send, send_bytes, device):
+    """Variable-size all-to-all of a flat uint8 tensor. Returns (recv tensor, per-source byte counts)."""
+    world = dist.get_world_size()
+    sc = torch.tensor(send_bytes, dtype=torch.int64, device=device)
+    rc = torch.empty_like(sc)
+    dist.all_to_all_single(rc, sc)
+    recv_bytes = rc.tolist()
+    recv = torch.empty(sum(recv_bytes), dtype=torch.uint8, device=device)
+    dist.all_to_all_single(recv, send, output_split_sizes=recv_bytes, input_split_sizes=list(send_bytes))
+    assert len(recv_bytes) == world
+    return recv, recv_bytes
+
+
+def exchange_round(eng, torch, dist, device):
+    """Ship the owner-grouped tuples of the chunk this rank just fed (or nothing) and insert what this rank owns."""
+    ptr, ranges, tb = eng.exchange_buffer()
+    send_bytes = split_sizes(ranges, tb)
+    total = ranges[-1] * tb
+    send = torch.as_tensor(DeviceMemory(ptr, total), device=device) if total else torch.empty(0, dtype=torch.uint8, device=device)
+    recv, recv_bytes = all_to_all_bytes(torch, dist, send, send_bytes, device)
+    n = sum(recv_bytes) // tb
+    if n:
+        eng.apply_tuples(recv.data_ptr(), n)
+    eng.exchange_clear()
+    return n
