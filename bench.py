@@ -225,7 +225,7 @@ def main():
     torch.cuda.synchronize()
     text_bytes = t1.numel() + t2.numel()
     est_distinct = int(args.genome * 2.3) + 1_000_000
-    slots = 1 << max(20, (int(est_distinct / world * 2.2)).bit_length())
+    slots = 1 << max(20, (int(est_distinct / world * 2.2 * float(os.environ.get('PGB200_BENCH_SLOTS_MULT', '1')))).bit_length())
     eng = api.PregraphEngine(K=K, P=8, initG=0, max_rd_len=RD_LEN, device=local_rank, table_slots=slots, world=world, rank=rank,
                              verbose=int(os.environ.get("PGB200_VERBOSE", "0")))
     chunk = args.chunk_reads * REC_BYTES

@@ -92,7 +92,12 @@ public:
     u64* h_cnt_ = nullptr;      // pinned mirror
 
     // decode scratch
-    DevBuf text_buf_, line_buf_, scan_buf_;
+    DevBuf text_bufs_[2], line_buf_, scan_buf_;
+    int text_flip_ = 0;
+    cudaStream_t st_copy_ = nullptr;   // H2D of chunk i+1 overlaps the insert of chunk i
+    cudaEvent_t ev_copy_ = nullptr;
+    bool timing_pending_ = false;
+    void settle_timing();
 
     // layout: reference geometry
     u64 set_size_ = 0;          // prime size of every reference set (static -a mode)
@@ -139,6 +144,11 @@ public:
 
     // helpers
     void ensure_table(u64 need_free);
+    void ensure_table_bound(u64 have, u64 incoming);
+    void create_table_if_needed();
+    std::vector<std::pair<void*, size_t>> arena_;   // read-store blocks
+    size_t arena_used_ = 0;
+    void* arena_alloc(size_t bytes);
     void grow_table(u64 new_cap);
     void alloc_table(u64 cap);
     void sync() { PG_CUDA(cudaStreamSynchronize(st_)); }

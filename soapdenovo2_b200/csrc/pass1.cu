@@ -16,6 +16,8 @@
 
 namespace pgb {
 
+static double host_now() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; }
+
 // ------------------------------------------------------------------------------------------------ K1: line index
 // element = one 16-byte group of the text; value = number of '\n' in it
 struct NlIn {
@@ -148,6 +150,9 @@ __global__ void __launch_bounds__(256) k_decode_pack(const unsigned char* __rest
 //  memory ring -- was measured and dropped: 38.6 ms vs 28.0 ms per 5.3e8 instances at every distance; the kernel is bound
 //  by the random-sector rate of L2/HBM, not by exposed latency.  profiles/r01_insert_ncu.md.)
 constexpr int INS_THREADS = 256;
+#ifndef INS_MIN_BLOCKS
+#define INS_MIN_BLOCKS 5
+#endif
 
 template <int NW>
 struct InsertSink {
@@ -160,7 +165,7 @@ struct InsertSink {
 };
 
 template <int NW>
-__global__ void __launch_bounds__(INS_THREADS) k_chop_insert(Table<NW> tab, KParams<NW> kp, const u64* __restrict__ words,
+__global__ void __launch_bounds__(INS_THREADS, INS_MIN_BLOCKS) k_chop_insert(Table<NW> tab, KParams<NW> kp, const u64* __restrict__ words,
                                                              const u32* __restrict__ lens, u64 n_rec, int W64, u64 ord_base, u64 ord_stride,
                                                              u64* counters) {
     __shared__ unsigned s_new;
@@ -221,23 +226,26 @@ void EngineT<NW>::grow_table(u64 new_cap) {
 }
 
 template <int NW>
-void EngineT<NW>::ensure_table(u64 incoming) {
-    if (!tab_.slots) {
-        u64 want = prm_.table_slots;
-        if (!want) {
-            if (prm_.initG) {
-                // the reference's own budget: P sets of the static prime size (prlHashReads.c:369-390)
-                want = (u64)prm_.P * ref_static_set_size(prm_.initG, prm_.P, prm_.flavour127 != 0);
-                want = want + want / 4;
-            } else {
-                want = 1ull << 24;
-            }
+void EngineT<NW>::create_table_if_needed() {
+    if (tab_.slots) return;
+    u64 want = prm_.table_slots;
+    if (!want) {
+        if (prm_.initG) {
+            // the reference's own budget: P sets of the static prime size (prlHashReads.c:369-390)
+            want = (u64)prm_.P * ref_static_set_size(prm_.initG, prm_.P, prm_.flavour127 != 0);
+            want = want + want / 4;
+        } else {
+            want = 1ull << 24;
         }
-        u64 cap = next_pow2(want < 1024 ? 1024 : want);
-        alloc_table(cap);
     }
-    read_counters();
-    u64 need = h_cnt_[C_DISTINCT] + incoming;   // every incoming instance could be a new key
+    alloc_table(next_pow2(want < 1024 ? 1024 : want));
+}
+
+// have = distinct keys already in the table (exact as of the last sync), incoming = upper bound of new keys about to arrive
+template <int NW>
+void EngineT<NW>::ensure_table_bound(u64 have, u64 incoming) {
+    create_table_if_needed();
+    u64 need = have + incoming;   // every incoming instance could be a new key
     if ((double)need <= 0.80 * (double)cap_) return;
     u64 cap = cap_;
     while ((double)need > 0.80 * (double)cap) cap <<= 1;
@@ -249,8 +257,30 @@ void EngineT<NW>::ensure_table(u64 incoming) {
         throw std::runtime_error("pgb200: k-mer table cannot grow further (out of HBM); use more GPUs or a smaller batch");
 }
 
+template <int NW>
+void EngineT<NW>::ensure_table(u64 incoming) {
+    create_table_if_needed();
+    read_counters();
+    ensure_table_bound(h_cnt_[C_DISTINCT], incoming);
+}
+
+// read-store arena: chunks are carved out of large blocks (no cudaMalloc / cudaFree per chunk)
+template <int NW>
+void* EngineT<NW>::arena_alloc(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (arena_.empty() || arena_used_ + bytes > arena_.back().second) {
+        size_t blk = std::max<size_t>(bytes, (size_t)1 << 30);
+        void* p = nullptr;
+        PG_CUDA(cudaMalloc(&p, blk));
+        arena_.push_back({p, blk});
+        arena_used_ = 0;
+    }
+    void* r = static_cast<char*>(arena_.back().first) + arena_used_;
+    arena_used_ += bytes;
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------ feed_text
-static double host_now() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; }
 
 template <int NW>
 void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int fastq, uint64_t ord_base, uint64_t ord_stride,
@@ -259,15 +289,23 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     last_records_ = 0;
     if (nbytes == 0) return;
     PG_CUDA(cudaSetDevice(prm_.device));
-    PG_CUDA(cudaEventRecord(ev_[0], st_));
     const unsigned char* d_text;
+    bool host_src = !on_device;
+    if (host_src) {
+        // H2D on its own stream into the buffer the previous chunk is NOT using: the copy overlaps the previous chunk's insert
+        DevBuf& tb = text_bufs_[text_flip_];
+        text_flip_ ^= 1;
+        tb.ensure(nbytes + 16);
+        PG_CUDA(cudaMemcpyAsync(tb.p, text, nbytes, cudaMemcpyHostToDevice, st_copy_));
+        PG_CUDA(cudaEventRecord(ev_copy_, st_copy_));
+        PG_CUDA(cudaStreamWaitEvent(st_, ev_copy_, 0));
+        d_text = tb.template as<unsigned char>();
+    }
+    settle_timing();   // previous chunk's events (waits for its insert; the copy above is already in flight)
+    PG_CUDA(cudaEventRecord(ev_[0], st_));
     if (on_device) {
         if ((uintptr_t)text & 15) throw std::runtime_error("pgb200: device text must be 16-byte aligned");
         d_text = reinterpret_cast<const unsigned char*>(text);
-    } else {
-        text_buf_.ensure(nbytes + 16);
-        PG_CUDA(cudaMemcpyAsync(text_buf_.p, text, nbytes, cudaMemcpyHostToDevice, st_));
-        d_text = text_buf_.template as<unsigned char>();
     }
     if (maxlen > prm_.max_rd_len) maxlen = prm_.max_rd_len;
     const int lpr = fastq ? 4 : 2;
@@ -276,12 +314,14 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     NlIn in{reinterpret_cast<const uint4*>(d_text), (u64)nbytes};
     // pass A: count lines
     device_scan(in, NlCountOut{}, groups, scan_buf_.template as<u64>(), d_cnt_ + C_MISC0, st_);
+    // ONE host sync per chunk: line count, last byte, and the counters as of the previous chunk's insert
+    unsigned char* h_last = reinterpret_cast<unsigned char*>(h_cnt_ + C_COUNT);
+    PG_CUDA(cudaMemcpyAsync(h_last, d_text + nbytes - 1, 1, cudaMemcpyDeviceToHost, st_));
     read_counters();
     u64 n_lines = h_cnt_[C_MISC0];
+    const u64 have_distinct = h_cnt_[C_DISTINCT];
     // a final line without '\n' still counts (the reference's FASTQ path tolerates it; its FASTA path does not)
-    unsigned char lastc;
-    PG_CUDA(cudaMemcpyAsync(&lastc, d_text + nbytes - 1, 1, cudaMemcpyDeviceToHost, st_));
-    sync();
+    unsigned char lastc = *h_last;
     bool open_tail = lastc != '\n';
     u64 n_rec = (n_lines + (open_tail ? 1 : 0)) / lpr;
     if ((n_lines + (open_tail ? 1 : 0)) % lpr != 0)
@@ -306,8 +346,8 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     ch.n_rec = n_rec;
     ch.ord_base = ord_base;
     ch.ord_stride = ord_stride;
-    PG_CUDA(cudaMalloc(&ch.words, n_rec * (u64)W64_ * sizeof(u64)));
-    PG_CUDA(cudaMalloc(&ch.len, n_rec * sizeof(u32)));
+    ch.words = reinterpret_cast<u64*>(arena_alloc(n_rec * (u64)W64_ * sizeof(u64)));
+    ch.len = reinterpret_cast<u32*>(arena_alloc(n_rec * sizeof(u32)));
     chunks_.push_back(ch);
     t_c = host_now();
     {
@@ -318,11 +358,11 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
         PG_CUDA(cudaGetLastError());
     }
     PG_CUDA(cudaEventRecord(ev_[1], st_));
-    // table capacity for the worst case of this chunk
-    u64 before_inst = h_cnt_[C_INSTANCES];
-    ensure_table(0);   // creates the table on first use, refreshes h_cnt_ (decode is complete after this sync)
-    u64 chunk_inst = h_cnt_[C_INSTANCES] - before_inst;
-    ensure_table(chunk_inst);
+    // table capacity for the worst case of this chunk (host-side bound: no sync; growth itself syncs when it happens)
+    {
+        int per_read = maxlen - prm_.K + 1;
+        ensure_table_bound(have_distinct, per_read > 0 ? n_rec * (u64)per_read : 0);
+    }
     t_d = host_now();
     if (l2gran_mode_ == 2) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     PG_CUDA(cudaEventRecord(ev_[2], st_));
@@ -337,22 +377,32 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
         PG_CUDA(cudaGetLastError());
     }
     PG_CUDA(cudaEventRecord(ev_[3], st_));
-    sync();
-    if (l2gran_mode_ == 2) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 128);
-    float ms;
-    PG_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1])); p1_.ms_decode += ms;
-    PG_CUDA(cudaEventElapsedTime(&ms, ev_[2], ev_[3])); p1_.ms_insert += ms;
+    timing_pending_ = true;
+    if (host_src) PG_CUDA(cudaEventSynchronize(ev_copy_));   // the caller may reuse its host buffer; the insert keeps running
+    else if (prm_.world > 1) sync();                          // exchange buffer is read by the caller next
+    if (l2gran_mode_ == 2) { sync(); cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 128); }
     p1_.launches += 8;
     last_records_ = n_rec;
     total_records_ += n_rec;
     t_e = host_now();
     if (prm_.verbose >= 2)
-        fprintf(stderr, "[pgb200] chunk %zu: %llu rec, host ms: count %.2f alloc %.2f decode+table %.2f insert %.2f (gpu: decode %.2f insert %.2f)\n", chunks_.size(),
+        fprintf(stderr, "[pgb200] chunk %zu: %llu rec, host ms: count %.2f alloc %.2f decode+table %.2f launch %.2f (gpu so far: decode %.2f insert %.2f)\n", chunks_.size(),
                 (unsigned long long)n_rec, t_b - t_a, t_c - t_b, t_d - t_c, t_e - t_d, p1_.ms_decode, p1_.ms_insert);
 }
 
 template <int NW>
+void EngineT<NW>::settle_timing() {
+    if (!timing_pending_) return;
+    PG_CUDA(cudaEventSynchronize(ev_[3]));
+    float ms;
+    PG_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1])); p1_.ms_decode += ms;
+    PG_CUDA(cudaEventElapsedTime(&ms, ev_[2], ev_[3])); p1_.ms_insert += ms;
+    timing_pending_ = false;
+}
+
+template <int NW>
 void EngineT<NW>::finish_pass1(Pass1Stats* st) {
+    settle_timing();
     read_counters();
     p1_.records = total_records_;
     p1_.reads_kept = h_cnt_[C_KEPT];
@@ -365,9 +415,13 @@ void EngineT<NW>::finish_pass1(Pass1Stats* st) {
 
 template <int NW>
 void EngineT<NW>::reset_pass1() {
+    double t0 = host_now();
+    settle_timing();
     sync();
-    for (auto& c : chunks_) { cudaFree(c.words); cudaFree(c.len); }
     chunks_.clear();
+    // keep the first arena block for the next pass, release the rest
+    while (arena_.size() > 1) { cudaFree(arena_.back().first); arena_.pop_back(); }
+    arena_used_ = 0;
     total_records_ = 0;
     p1_ = Pass1Stats();
     PG_CUDA(cudaMemsetAsync(d_cnt_, 0, C_COUNT * sizeof(u64), st_));
@@ -376,6 +430,7 @@ void EngineT<NW>::reset_pass1() {
     n_nodes_ = 0;
     sync();
     h_cnt_[C_DISTINCT] = h_cnt_[C_INSTANCES] = 0;
+    if (prm_.verbose >= 2) fprintf(stderr, "[pgb200] reset_pass1: %.2f ms host\n", host_now() - t0);
 }
 
 // ------------------------------------------------------------------------------------------------ K4: sweeps
@@ -416,6 +471,7 @@ __global__ void __launch_bounds__(256) k_sweep(Table<NW> tab, int D, u64* hist, 
 
 template <int NW>
 void EngineT<NW>::sweeps(SweepStats* st) {
+    double t0 = host_now();
     DevBuf hist;
     hist.alloc(256 * sizeof(u64));
     PG_CUDA(cudaMemsetAsync(hist.p, 0, 256 * sizeof(u64), st_));
@@ -429,6 +485,7 @@ void EngineT<NW>::sweeps(SweepStats* st) {
     for (int i = 0; i < 256; i++) st->hist[i] = (long long)h[i];
     st->linear = h_cnt_[C_LINEAR];
     st->removed = h_cnt_[C_REMOVED];
+    if (prm_.verbose >= 2) fprintf(stderr, "[pgb200] sweeps: %.2f ms host\n", host_now() - t0);
 }
 
 // ------------------------------------------------------------------------------------------------ ctor / dtor
@@ -442,10 +499,12 @@ EngineT<NW>::EngineT(const PgParams& p) : prm_(p) {
     if (l2gran_mode_ == 1) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     kp_ = make_kparams<NW>(p.K);
     PG_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    PG_CUDA(cudaStreamCreateWithFlags(&st_copy_, cudaStreamNonBlocking));
+    PG_CUDA(cudaEventCreateWithFlags(&ev_copy_, cudaEventDisableTiming));
     for (auto& e : ev_) PG_CUDA(cudaEventCreate(&e));
     PG_CUDA(cudaMalloc(&d_cnt_, C_COUNT * sizeof(u64)));
     PG_CUDA(cudaMemsetAsync(d_cnt_, 0, C_COUNT * sizeof(u64), st_));
-    PG_CUDA(cudaHostAlloc(&h_cnt_, C_COUNT * sizeof(u64), cudaHostAllocDefault));
+    PG_CUDA(cudaHostAlloc(&h_cnt_, (C_COUNT + 2) * sizeof(u64), cudaHostAllocDefault));
     for (int i = 0; i < C_COUNT; i++) h_cnt_[i] = 0;
     W64_ = (p.max_rd_len + 31) / 32;
     if (W64_ < 1) W64_ = 1;
@@ -455,10 +514,12 @@ EngineT<NW>::EngineT(const PgParams& p) : prm_(p) {
 template <int NW>
 EngineT<NW>::~EngineT() {
     cudaStreamSynchronize(st_);
-    for (auto& c : chunks_) { cudaFree(c.words); cudaFree(c.len); }
+    for (auto& a : arena_) cudaFree(a.first);
     if (d_cnt_) cudaFree(d_cnt_);
     if (h_cnt_) cudaFreeHost(h_cnt_);
     for (auto& e : ev_) if (e) cudaEventDestroy(e);
+    if (ev_copy_) cudaEventDestroy(ev_copy_);
+    if (st_copy_) cudaStreamDestroy(st_copy_);
     if (st_) cudaStreamDestroy(st_);
 }
 

@@ -3,8 +3,8 @@
 // Used for: newline -> line index (decode.cu), occupancy -> position in reference iteration order (layout.cu),
 // per-edge text lengths / edge ids (edges.cu), per-read record offsets (pass2.cu).
 // Three launches per level: tile sums -> (recursive) scan of the tile sums -> rescan tiles with their base.
-// A tile is SCAN_THREADS x SCAN_ITEMS consecutive elements, read coalesced (thread t takes items t, t+T, ...
-// inside each of SCAN_ITEMS strips), so the pass is a pure streaming read at HBM speed.
+// A tile is SCAN_THREADS x SCAN_ITEMS consecutive elements; thread t owns items [t*ITEMS, (t+1)*ITEMS) so a tile needs one
+// block-wide scan (the per-thread runs are contiguous 256 B pieces for 16-byte elements: sector-efficient streaming).
 #pragma once
 #include "kmer.cuh"
 #include <cuda_runtime.h>
@@ -46,13 +46,14 @@ __device__ __forceinline__ u64 block_exclusive_scan(u64 v, u64* total) {
     return r;
 }
 
+// Each thread owns SCAN_ITEMS CONSECUTIVE elements of the tile (one block-wide scan per tile instead of one per strip).
 template <class In>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(In in, u64 n, u64* sums) {
-    u64 base = (u64)blockIdx.x * SCAN_TILE;
+    u64 first = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
     u64 acc = 0;
 #pragma unroll 4
     for (int s = 0; s < SCAN_ITEMS; s++) {
-        u64 i = base + (u64)s * SCAN_THREADS + threadIdx.x;
+        u64 i = first + s;
         if (i < n) acc += in(i);
     }
     u64 tot;
@@ -62,15 +63,23 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(In in, u64 n, u
 
 template <class In, class Out>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(In in, Out out, u64 n, const u64* tile_base) {
-    u64 base = (u64)blockIdx.x * SCAN_TILE;
-    u64 running = tile_base[blockIdx.x];
+    u64 first = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
+    u64 v[SCAN_ITEMS];
+    u64 acc = 0;
+#pragma unroll
     for (int s = 0; s < SCAN_ITEMS; s++) {
-        u64 i = base + (u64)s * SCAN_THREADS + threadIdx.x;
-        u64 v = i < n ? in(i) : 0;
-        u64 tot;
-        u64 ex = block_exclusive_scan(v, &tot);
-        if (i < n) out(i, running + ex, v);
-        running += tot;
+        u64 i = first + s;
+        u64 x = i < n ? in(i) : 0;
+        v[s] = x;
+        acc += x;
+    }
+    u64 tot;
+    u64 running = tile_base[blockIdx.x] + block_exclusive_scan(acc, &tot);
+#pragma unroll
+    for (int s = 0; s < SCAN_ITEMS; s++) {
+        u64 i = first + s;
+        if (i < n) out(i, running, v[s]);
+        running += v[s];
     }
 }
 

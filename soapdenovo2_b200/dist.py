@@ -41,6 +41,10 @@ def exchange_round(eng, torch, dist, device):
     total = ranges[-1] * tb
     send = torch.as_tensor(DeviceMemory(ptr, total), device=device) if total else torch.empty(0, dtype=torch.uint8, device=device)
     recv, recv_bytes = all_to_all_bytes(torch, dist, send, send_bytes, device)
+    if recv.is_cuda:
+        # the collective runs on torch's NCCL stream, the engine on its own stream: the received tuples must have landed (and
+        # the send buffer must be free for the next chunk) before the engine touches either
+        torch.cuda.current_stream(recv.device).synchronize()
     n = sum(recv_bytes) // tb
     if n:
         eng.apply_tuples(recv.data_ptr(), n)
