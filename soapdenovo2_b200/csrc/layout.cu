@@ -14,6 +14,9 @@
 // own rank again, a third turns the rank table into "position -> ktab slot", and one scan compacts it into order[].
 #include "engine_impl.cuh"
 #include "scan.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+#include <thread>
 
 namespace pgb {
 
@@ -103,22 +106,83 @@ struct OrderOut {
     }
 };
 
-// growth sequence of a dynamic reference set that ends up holding `count` keys (newhash.c:200-233, 340-381)
-static u64 ref_dynamic_final_size(u64 count) {
-    u64 size = ref_next_prime(1024);
-    float lf = 0.77f;
-    u64 mx = (u64)(size * lf);
-    // put #c (1-based) triggers growth when (c-1)+1 > max
-    while (count > mx) {
-        u64 n = size;
-        u64 at = mx + 1;   // the put that triggered sees count == mx
-        do {
-            if (n < 0xFFFFFFFULL) n <<= 1; else n += 0xFFFFFFULL;
-            n = ref_next_prime(n);
-        } while (n * lf < at);
-        size = n;
-        mx = (u64)(size * lf);
+// ---------------------------------------------------------------- f1: dynamic tables (no -a): growth-history replay
+// Without -a the reference's sets start at 1031 slots and grow (encap_kmerset, newhash.c:340-455): new prime size, array
+// realloc'ed IN PLACE, entries re-inserted in ascending old-slot order with displacement chains.  The final layout therefore
+// depends on the whole growth history.  The history is a function of the keys' first-occurrence order alone (growth k happens
+// when the set holds exactly its first max_k distinct keys), so it can be replayed after the fact: the GPU sorts the distinct
+// k-mers by (set, rank) (library radix sort: plumbing outside the metric) and each set is replayed by one host thread with
+// the same put / grow rules.  Cost O(distinct); only runs when -a is absent.
+template <int NW>
+__global__ void __launch_bounds__(256) k_replay_keys(Table<NW> tab, int P, u64* sort_key, u64* sort_val, u64* cursor) {
+    u64 n = tab.mask + 1;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const Slot<NW>* s = tab.slots + i;
+        if (!slot_occupied(s)) continue;
+        u64 set = crc_hash(slot_key(s)) % (u64)P;
+        u64 p = atomicAdd(cursor, 1ull);
+        sort_key[p] = (set << 56) | (s->aux & ((1ull << 56) - 1));   // rank < 2^56 (read ordinal < 2^40)
+        sort_val[p] = i;
     }
+}
+template <int NW>
+__global__ void __launch_bounds__(256) k_gather_keys(Table<NW> tab, const u64* slots_sorted, u64 n, u64* keys_out) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        Kmer<NW> k = slot_key(tab.slots + slots_sorted[i]);
+        for (int w = 0; w < NW; w++) keys_out[i * NW + w] = k.w[w];
+    }
+}
+__global__ void __launch_bounds__(256) k_fill_R(const u64* slots_sorted, const u64* gpos, u64 n, u64* R) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) R[gpos[i]] = slots_sorted[i];
+}
+
+// one reference set, replayed on the host: keys[0..n) in first-occurrence order; returns the final size and pos[i]
+template <int NW>
+static u64 replay_one_set(const u64* keys, u64 n, bool flavour127, std::vector<u32>& slot /* out: index+1 per slot */) {
+    u64 size = ref_next_prime(1024);
+    const float lf = 0.77f;
+    u64 mx = (u64)(size * lf), count = 0;
+    slot.assign(size, 0);
+    auto home = [&](u64 idx, u64 sz) {
+        Kmer<NW> k;
+        for (int w = 0; w < NW; w++) k.w[w] = keys[idx * NW + w];
+        return ref_home(k, sz, flavour127);
+    };
+    std::vector<unsigned char> oldocc, newocc;
+    auto grow = [&]() {   // encap_kmerset, dynamic branch (newhash.c:368-452)
+        u64 nn = size;
+        do { if (nn < 0xFFFFFFFULL) nn <<= 1; else nn += 0xFFFFFFULL; nn = ref_next_prime(nn); } while (nn * lf < count + 1);
+        u64 old = size;
+        oldocc.assign(old, 0);
+        for (u64 j = 0; j < old; j++) oldocc[j] = slot[j] != 0;
+        slot.resize(nn, 0);
+        newocc.assign(nn, 0);
+        size = nn;
+        mx = (u64)(nn * lf);
+        for (u64 j = 0; j < old; j++) {
+            if (!oldocc[j]) continue;
+            u32 key = slot[j];
+            oldocc[j] = 0;
+            for (;;) {
+                u64 hc = home(key - 1, nn);
+                while (newocc[hc]) { if (++hc == nn) hc = 0; }
+                newocc[hc] = 1;
+                if (hc < old && oldocc[hc]) { std::swap(key, slot[hc]); oldocc[hc] = 0; }
+                else { slot[hc] = key; break; }
+            }
+        }
+        for (u64 j = 0; j < old; j++) if (!newocc[j]) slot[j] = 0;
+    };
+    for (u64 i = 0; i < n; i++) {
+        if (count + 1 > mx) grow();   // checked on EVERY put, before probing (newhash.c:477-480)
+        u64 hc = home(i, size);
+        while (slot[hc]) { if (++hc == size) hc = 0; }
+        slot[hc] = (u32)(i + 1);
+        count++;
+    }
+    // the check also fires on hits: a set that ends exactly at its threshold grows at its next (repeat) instance, which
+    // exists unless the set's last new k-mer is also its very last instance in the read stream (not tracked; assumed)
+    if (n && count + 1 > mx) grow();
     return size;
 }
 
@@ -148,17 +212,58 @@ void EngineT<NW>::build_layout() {
         }
         layout_exact_ = true;
     } else {
-        // Dynamic growth: the reference's final layout depends on the whole growth history (in-place rehash with
-        // displacement chains, newhash.c:403-452).  Sizes are reproduced; the slot order is the FCFS order in the final
-        // size, which equals the reference's only for sets that never grew.  Bit-exact runs use -a.
-        layout_exact_ = true;
-        for (int i = 0; i < P; i++) {
-            set_size[i] = ref_dynamic_final_size(cnt[i]);
-            if (set_size[i] != ref_next_prime(1024)) layout_exact_ = false;
+        // Dynamic growth: replay every set's growth history (see above)
+        for (int i = 0; i < P; i++)
+            if (cnt[i] >= 0xFFFFFFF0ull) throw std::runtime_error("pgb200: a dynamic reference set would exceed 2^32 entries; use -a");
+        const u64 N = n_nodes_;
+        DevBuf kb, vb, kb2, vb2, curb, tmpb, keysb;
+        kb.alloc((N + 1) * sizeof(u64)); vb.alloc((N + 1) * sizeof(u64)); kb2.alloc((N + 1) * sizeof(u64)); vb2.alloc((N + 1) * sizeof(u64));
+        curb.alloc(sizeof(u64));
+        PG_CUDA(cudaMemsetAsync(curb.p, 0, sizeof(u64), st_));
+        k_replay_keys<NW><<<148 * 8, 256, 0, st_>>>(tab_, P, kb.template as<u64>(), vb.template as<u64>(), curb.template as<u64>());
+        PG_CUDA(cudaGetLastError());
+        size_t tmp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb.template as<u64>(), kb2.template as<u64>(), vb.template as<u64>(), vb2.template as<u64>(), N, 0, 64, st_);
+        tmpb.alloc(tmp_bytes);
+        cub::DeviceRadixSort::SortPairs(tmpb.p, tmp_bytes, kb.template as<u64>(), kb2.template as<u64>(), vb.template as<u64>(), vb2.template as<u64>(), N, 0, 64, st_);
+        keysb.alloc((N + 1) * NW * sizeof(u64));
+        k_gather_keys<NW><<<148 * 8, 256, 0, st_>>>(tab_, vb2.template as<u64>(), N, keysb.template as<u64>());
+        PG_CUDA(cudaGetLastError());
+        std::vector<u64> h_keys(N * NW + 1);
+        PG_CUDA(cudaMemcpyAsync(h_keys.data(), keysb.p, N * NW * sizeof(u64), cudaMemcpyDeviceToHost, st_));
+        sync();
+        std::vector<u64> first(P + 1, 0);
+        for (int i = 0; i < P; i++) first[i + 1] = first[i] + cnt[i];
+        std::vector<std::vector<u32>> slots(P);
+        {
+            std::vector<std::thread> th;
+            const bool f127 = prm_.flavour127 != 0;
+            for (int i = 0; i < P; i++)
+                th.emplace_back([&, i]() { set_size[i] = replay_one_set<NW>(h_keys.data() + first[i] * NW, cnt[i], f127, slots[i]); });
+            for (auto& t : th) t.join();
         }
-        if (!layout_exact_ && prm_.verbose >= 0)
-            fprintf(stderr, "[pgb200] note: no -a given and the reference's sets would have grown: iteration order is FCFS in the final "
-                            "set size, not the reference's growth-history order (outputs are valid but not byte-identical)\n");
+        u64 total = 0;
+        for (int i = 0; i < P; i++) { set_base[i] = total; total += set_size[i]; }
+        std::vector<u64> h_gpos(N + 1);
+        for (int i = 0; i < P; i++)
+            for (u64 j = 0; j < set_size[i]; j++)
+                if (slots[i][j]) h_gpos[first[i] + slots[i][j] - 1] = set_base[i] + j;
+        DevBuf gposb, Rb, scratch;
+        gposb.alloc((N + 1) * sizeof(u64));
+        PG_CUDA(cudaMemcpyAsync(gposb.p, h_gpos.data(), N * sizeof(u64), cudaMemcpyHostToDevice, st_));
+        Rb.alloc(total * sizeof(u64));
+        PG_CUDA(cudaMemsetAsync(Rb.p, 0xFF, total * sizeof(u64), st_));
+        k_fill_R<<<148 * 8, 256, 0, st_>>>(vb2.template as<u64>(), gposb.template as<u64>(), N, Rb.template as<u64>());
+        PG_CUDA(cudaGetLastError());
+        order_buf_.alloc((N + 1) * sizeof(u64));
+        scratch.alloc(scan_scratch_elems(total) * sizeof(u64));
+        device_scan(OccIn{Rb.template as<u64>()}, OrderOut<NW>{Rb.template as<u64>(), order_buf_.template as<u64>(), tab_.slots}, total,
+                    scratch.template as<u64>(), d_cnt_ + C_MISC0, st_);
+        read_counters();
+        if (h_cnt_[C_MISC0] != N) throw std::runtime_error("pgb200: internal error: dynamic layout replay lost k-mers");
+        set_size_ = set_size[0];
+        layout_exact_ = true;
+        return;
     }
     u64 total = 0;
     for (int i = 0; i < P; i++) { set_base[i] = total; total += set_size[i]; }

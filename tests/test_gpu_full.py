@@ -109,3 +109,19 @@ def test_midsize_pe_k63_vs_reference(tmp_path):
     util.compare(ref, gpu, util.SUFFIXES_R)
     if util.have_ref():
         assert _counter_lines(lr) == _counter_lines(lg)
+
+
+@pytest.mark.parametrize("K,P,extra", [(31, 3, ("-R",)), (31, 8, ()), (31, 1, ("-d", "1"))])
+def test_dynamic_tables_no_a(se_cfg, tmp_path, K, P, extra):
+    """f1: without -a the reference's sets grow (in-place rehash with displacement chains); the engine replays the growth history."""
+    ref, gpu = str(tmp_path / "ref"), str(tmp_path / "gpu")
+    _oracle(0, se_cfg, ref, K, P, extra)
+    _engine(0, se_cfg, gpu, K, P, extra)
+    util.compare(ref, gpu, util.SUFFIXES_R if "-R" in extra else util.SUFFIXES)
+
+
+def test_dynamic_tables_no_a_pe_127(pe_cfg, tmp_path):
+    ref, gpu = str(tmp_path / "ref"), str(tmp_path / "gpu")
+    _oracle(1, pe_cfg, ref, 127, 4, ("-R",))
+    _engine(1, pe_cfg, gpu, 127, 4, ("-R",))
+    util.compare(ref, gpu, util.SUFFIXES_R)
