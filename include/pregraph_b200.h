@@ -66,7 +66,7 @@ void *pgb200_host_alloc(size_t bytes);
 void pgb200_host_free(void *p);
 
 /* Pass 1.  `text` holds whole FASTA (single-line) or FASTQ (4-line) records, starts at a record start, ends with '\n'.
- * on_device != 0: `text` is a device pointer (16-byte aligned).  Record i gets stream ordinal ord_base + i*ord_stride
+ * on_device != 0: `text` is a device pointer (any alignment; 16-byte aligned pointers avoid one device-to-device copy).  Record i gets stream ordinal ord_base + i*ord_stride
  * (stride 2 + mate offset for f1/f2, q1/q2 files: the reference interleaves mates, prlHashReads.c:480-583).       */
 int pgb200_feed_text(pgb200_engine *e, const char *text, size_t nbytes, int on_device, int fastq, uint64_t ord_base,
                      uint64_t ord_stride, int reverse_seq, int maxlen);

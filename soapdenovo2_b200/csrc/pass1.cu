@@ -304,8 +304,14 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     settle_timing();   // previous chunk's events (waits for its insert; the copy above is already in flight)
     PG_CUDA(cudaEventRecord(ev_[0], st_));
     if (on_device) {
-        if ((uintptr_t)text & 15) throw std::runtime_error("pgb200: device text must be 16-byte aligned");
         d_text = reinterpret_cast<const unsigned char*>(text);
+        if ((uintptr_t)text & 15) {   // the line index reads 16-byte groups: realign with one device-to-device copy
+            DevBuf& tb = text_bufs_[text_flip_];
+            text_flip_ ^= 1;
+            tb.ensure(nbytes + 16);
+            PG_CUDA(cudaMemcpyAsync(tb.p, text, nbytes, cudaMemcpyDeviceToDevice, st_));
+            d_text = tb.template as<unsigned char>();
+        }
     }
     if (maxlen > prm_.max_rd_len) maxlen = prm_.max_rd_len;
     const int lpr = fastq ? 4 : 2;

@@ -157,3 +157,48 @@ def scenario_multilib(d: str, genome_len=40000, seed=5) -> str:
         {"avg_ins": 300, "asm_flags": 2, "files": [("f", j("m_ig.fa"))]},
     ])
     return cfg
+
+
+def scenario_adversarial(d: str, seed=9, crlf=False, K_hint=31) -> str:
+    """Edge cases the reference's readers / counters / edge builder care about: ragged read lengths (incl. shorter than K+1
+    and exactly K+1), N's, lower case, '.', a poly-A stretch (counter saturation: links 63, coverage 255), tandem repeats,
+    a reverse-complement palindrome (bal_edge = 0 edges), optional CRLF line ends (the '\\r' is dropped, readseq1by1.c:182-200)."""
+    rng = np.random.default_rng(seed)
+    g = genome(12000, seed)
+    unit = g[100:137].copy()
+    g[3000:3000 + 37 * 6] = np.tile(unit, 6)                       # tandem repeat
+    g[5000:5400] = ord("A")                                         # poly-A
+    half = g[7000:7150].copy()
+    g[7150:7300] = _COMP[half[::-1]]                                # palindrome: half + revcomp(half)
+    nl = b"\r\n" if crlf else b"\n"
+    reads = []
+    for i in range(3500):
+        L = int(rng.choice([K_hint - 3, K_hint, K_hint + 1, K_hint + 2, 60, 75, 100, 100, 100]))
+        s = int(rng.integers(0, len(g) - L))
+        r = g[s:s + L].copy()
+        if rng.random() < 0.5:
+            r = _COMP[r[::-1]]
+        m = rng.random(L) < 0.004
+        r[m] = _ACGT[rng.integers(0, 4, size=int(m.sum()))]
+        if rng.random() < 0.05:
+            r[int(rng.integers(0, L))] = ord("N")
+        if rng.random() < 0.05:
+            r[int(rng.integers(0, L))] = ord(".")
+        if rng.random() < 0.2:
+            r = np.frombuffer(r.tobytes().lower(), dtype=np.uint8).copy()
+        reads.append(r.tobytes())
+    for i in range(600):                                            # deep poly-A coverage -> saturated counters
+        reads.append(b"A" * int(rng.choice([80, 100])))
+    order = rng.permutation(len(reads))
+    fa, fq = os.path.join(d, "adv.fa"), os.path.join(d, "adv.fq")
+    with open(fa, "wb") as f:
+        for j in order[: len(order) // 2]:
+            f.write(b">r%d" % j + nl + reads[j] + nl)
+    with open(fq, "wb") as f:
+        for j in order[len(order) // 2:]:
+            f.write(b"@r%d" % j + nl + reads[j] + nl + b"+" + nl + b"I" * len(reads[j]) + nl)
+    for p in (fa, fq):
+        _pad_if_32k(p)
+    cfg = os.path.join(d, "adv.cfg")
+    write_config(cfg, 100, [{"avg_ins": 200, "files": [("f", fa), ("q", fq)]}])
+    return cfg

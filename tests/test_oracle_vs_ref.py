@@ -65,3 +65,13 @@ def test_k_fixups(se_cfg, tmp_path):
         util.run_ref(util.REF63, se_cfg, ref, k, 2)
         util.run_model(util.MODEL63, se_cfg, mod, k, 2)
         util.compare(ref, mod, util.SUFFIXES)
+
+
+@pytest.mark.parametrize("crlf,K,P,extra", [(False, 31, 3, ("-R",)), (True, 31, 8, ("-a", "1", "-d", "2")), (True, 63, 4, ("-a", "1", "-R"))])
+def test_adversarial_inputs(tmp_path, crlf, K, P, extra):
+    """ragged lengths (< K+1, == K+1), N / '.' / lower case, poly-A saturation, tandem repeat, palindrome, CRLF."""
+    cfg = synth.scenario_adversarial(str(tmp_path), crlf=crlf, K_hint=K)
+    ref, mod = str(tmp_path / "ref"), str(tmp_path / "mod")
+    util.run_ref(util.REF63, cfg, ref, K, P, extra)
+    util.run_model(util.MODEL63, cfg, mod, K, P, extra)
+    util.compare(ref, mod, util.SUFFIXES_R if "-R" in extra else util.SUFFIXES)
