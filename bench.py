@@ -245,13 +245,16 @@ def main():
                 n = min(chunk, total - off)
                 work.append((base + off, n, (off // REC_BYTES) * 2 + mate))
                 off += n
+        pipe = pdist.PipelinedExchange(eng, torch, dist, dev) if world > 1 else None
         for r0 in range(0, len(work), world):
             i = r0 + rank
             if i < len(work):
                 ptr, n, ob = work[i]
                 eng.feed_text(ptr, n, on_device=on_device, fastq=True, ord_base=ob, ord_stride=2)
-            if world > 1:
-                pdist.exchange_round(eng, torch, dist, dev)
+            if pipe:
+                pipe.round()
+        if pipe:
+            pipe.finish()
         st = eng.finish_pass1()
         hist, lin, rem = eng.sweeps()   # D2H of the histogram + counters: the step's result
         return st, hist

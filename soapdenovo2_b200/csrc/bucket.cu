@@ -181,10 +181,11 @@ void EngineT<NW>::bucket_chunk(const ReadChunk& ch) {
     if (n_tuples_ >= 0xFFFFFFFFull) throw std::runtime_error("pgb200: more than 2^32 k-mer instances in one chunk; feed smaller chunks");
     owner_start_.assign(world + 1, n_tuples_);
     for (int o = 0; o < world; o++) owner_start_[o] = first_row[(size_t)o << rb];
-    tuple_buf_.ensure((n_tuples_ + 1) * TupleW<NW>::value * sizeof(u64));
+    tuple_flip_ ^= 1;
+    tuple_buf().ensure((n_tuples_ + 1) * TupleW<NW>::value * sizeof(u64));
     k_bucket_scatter<NW><<<(unsigned)n_tiles, BK_THREADS, smem, st_>>>(kp_, ch.words, ch.len, ch.n_rec, W64_, ch.ord_base, ch.ord_stride, tab_.mask,
                                                                        region_shift, rb, world, NB, tileoff_buf_.template as<u32>(),
-                                                                       tuple_buf_.template as<u64>());
+                                                                       tuple_buf().template as<u64>());
     PG_CUDA(cudaGetLastError());
     p1_.launches += 5;
 }

@@ -79,6 +79,7 @@ public:
     cudaStream_t st_ = nullptr;
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     int W64_ = 0;   // packed words per read
+    int insert_sm_ = 1;     // PGB200_INSERT_SM=0: the lock-step k_chop_insert instead of the per-lane state machine (K <= 63)
     int l2gran_mode_ = 0;   // PGB200_L2GRAN: 0 default, 1 = 32 B globally, 2 = 32 B only around k_chop_insert
 
     std::vector<ReadChunk> chunks_;
@@ -112,7 +113,9 @@ public:
 
     // bucketed insert path (bucket.cu): tuples {key words, meta} grouped by (owner GPU, table region)
     int bucket_mode_ = 0;       // PGB200_BUCKET=1: single-GPU inserts also go through the bucketed (region-sorted) path
-    DevBuf tuple_buf_, tilecnt_buf_, tileoff_buf_;
+    DevBuf tuple_bufs_[2], tilecnt_buf_, tileoff_buf_;   // two tuple buffers: chunk i+1 is bucketed while chunk i is on the wire
+    int tuple_flip_ = 0;
+    DevBuf& tuple_buf() { return tuple_bufs_[tuple_flip_]; }
     u64 n_tuples_ = 0;          // tuples currently in tuple_buf_
     int n_buckets_ = 0, region_bits_ = 0;
     std::vector<u64> owner_start_;   // [world + 1] tuple offsets of each owner's range in tuple_buf_
@@ -126,7 +129,7 @@ public:
         for (int o = 0; o <= world; o++) ranges[o] = owner_start_.size() == (size_t)world + 1 ? owner_start_[o] : 0;
         *tuple_bytes = tuple_words() * 8;
         sync();
-        return tuple_buf_.p;
+        return tuple_buf().p;
     }
     void exchange_clear() override { owner_start_.clear(); n_tuples_ = 0; }
     void apply_received(const void* tuples, uint64_t n) override {

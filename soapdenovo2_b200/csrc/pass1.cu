@@ -183,6 +183,102 @@ __global__ void __launch_bounds__(INS_THREADS, INS_MIN_BLOCKS) k_chop_insert(Tab
     if (threadIdx.x == 0 && s_new) atomicAdd(&counters[C_DISTINCT], (u64)s_new);
 }
 
+// ------------------------------------------------------------------------------------------------ K2+K3, state-machine form
+// ncu on k_chop_insert: ~85 % of stall samples wait on the slot load / CAS, and a quarter of them sit on instructions that only
+// 1-2 lanes execute (second probes, claims, CAS retries): with one read per lane, every k-mer position costs the WARP
+// max-over-lanes(probes) + claim + max-over-lanes(CAS tries) ~ 6 dependent round trips although a lane needs ~2.2 on average.
+// Here every lane runs its own state machine (ADVANCE -> PROBE -> [CLAIM] -> APPLY -> ADVANCE ...) and each trip round the loop
+// issues exactly ONE memory operation per lane, whatever its state; lanes drift apart by a few positions instead of
+// waiting for each other, so a round trip is spent on ~32 useful operations instead of 1-2.
+enum { ST_ADV = 0, ST_PROBE = 1, ST_CLAIM = 2, ST_APPLY = 3 };
+
+__global__ void __launch_bounds__(INS_THREADS) k_chop_insert_sm2(Table<2> tab, KParams<2> kp, const u64* __restrict__ words,
+                                                                 const u32* __restrict__ lens, u64 n_rec, int W64, u64 ord_base, u64 ord_stride,
+                                                                 u64* counters) {
+    __shared__ unsigned s_new;
+    if (threadIdx.x == 0) s_new = 0;
+    __syncthreads();
+    const int K = kp.K;
+    unsigned my_new = 0;
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += (u64)gridDim.x * blockDim.x) {
+        const int L = (int)lens[r];
+        if (L < K + 1) continue;
+        const u64* wp = words + r * (u64)W64;
+        const u64 rank_base = (ord_base + r * ord_stride) << 16;
+        Kmer<2> fwd = kzero<2>(), rc = kzero<2>();
+        u64 curw = wp[0];
+        int i = 0;
+        // pre-roll the first K-1 bases (no k-mer yet)
+        for (; i < K - 1; i++) {
+            if (i && (i & 31) == 0) curw = wp[i >> 5];
+            unsigned c = (unsigned)((curw >> (2 * (i & 31))) & 3);
+            fwd = knext(fwd, c, kp);
+            rc = kprev(rc, c ^ 2u, kp);
+        }
+        int state = ST_ADV;
+        Kmer<2> canon = kzero<2>();
+        u64 idx = 0, cur_p = 0, cur_r = 0, nxt_p = 0, rank = 0;
+        unsigned left = 4, right = 4;
+        for (;;) {
+            if (state == ST_ADV) {
+                if (i >= L) break;
+                if ((i & 31) == 0) curw = wp[i >> 5];
+                unsigned c = (unsigned)((curw >> (2 * (i & 31))) & 3);
+                unsigned cn = 4;
+                if (i + 1 < L) {
+                    u64 w2 = ((i + 1) & 31) == 0 ? wp[(i + 1) >> 5] : curw;
+                    cn = (unsigned)((w2 >> (2 * ((i + 1) & 31))) & 3);
+                }
+                unsigned dropped = kfirst(fwd, kp);
+                fwd = knext(fwd, c, kp);
+                rc = kprev(rc, c ^ 2u, kp);
+                int j = i - K + 1;
+                unsigned pv = j > 0 ? dropped : 4u;
+                bool sm = kless(fwd, rc);
+                canon = sm ? fwd : rc;
+                left = sm ? pv : (cn < 4 ? (cn ^ 2u) : 4u);
+                right = sm ? cn : (pv < 4 ? (pv ^ 2u) : 4u);
+                rank = rank_base | (u64)j;
+                idx = table_hash(canon) & tab.mask;
+                state = ST_PROBE;
+                i++;
+            }
+            // ---- issue: one memory operation per lane
+            Slot<2>* s = tab.slots + idx;
+            U256 v;
+            U128 o128;
+            u64 o64 = 0;
+            v.a = v.b = v.c = v.d = 0;
+            o128.a = o128.b = 0;
+            ld256_if(state == ST_PROBE, s, v);
+            cas128_if(state == ST_CLAIM, s->key, U128{EMPTY64, EMPTY64}, U128{canon.w[0], canon.w[1]}, o128);
+            cas64_if(state == ST_APPLY, &s->payload, cur_p, nxt_p, o64);
+            // ---- consume
+            bool have_cur = false;
+            if (state == ST_PROBE) {
+                if (v.a == canon.w[0] && v.b == canon.w[1]) { cur_p = v.c; cur_r = v.d; have_cur = true; }
+                else if (v.a == EMPTY64 && v.b == EMPTY64) state = ST_CLAIM;
+                else idx = (idx + 1) & tab.mask;
+            } else if (state == ST_CLAIM) {
+                if (o128.a == EMPTY64 && o128.b == EMPTY64) { my_new++; cur_p = PAYLOAD_FRESH; cur_r = EMPTY64; have_cur = true; }
+                else if (o128.a == canon.w[0] && o128.b == canon.w[1]) state = ST_PROBE;      // somebody else just claimed it for this key
+                else { idx = (idx + 1) & tab.mask; state = ST_PROBE; }
+            } else {   // ST_APPLY
+                if (o64 == cur_p) { if (rank < cur_r) atomicMin(&s->aux, rank); state = ST_ADV; }
+                else { cur_p = o64; have_cur = true; }
+            }
+            if (have_cur) {
+                nxt_p = payload_apply(cur_p, left, right);
+                if (nxt_p == cur_p) { if (rank < cur_r) atomicMin(&s->aux, rank); state = ST_ADV; }   // saturated: read-only
+                else state = ST_APPLY;
+            }
+        }
+    }
+    if (my_new) atomicAdd(&s_new, my_new);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_new) atomicAdd(&counters[C_DISTINCT], (u64)s_new);
+}
+
 // ------------------------------------------------------------------------------------------------ table management
 template <int NW>
 __global__ void k_rehash(Table<NW> oldt, Table<NW> newt) {
@@ -376,10 +472,14 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
         bucket_chunk(ch);                       // tuples stay in the exchange buffer: caller runs the all-to-all
     } else if (bucket_mode_) {
         bucket_chunk(ch);
-        apply_tuples(tuple_buf_.template as<u64>(), n_tuples_);
+        apply_tuples(tuple_buf().template as<u64>(), n_tuples_);
     } else {
         unsigned blocks = (unsigned)std::min<u64>((n_rec + INS_THREADS - 1) / INS_THREADS, 148ull * 64);
-        k_chop_insert<NW><<<blocks, INS_THREADS, 0, st_>>>(tab_, kp_, ch.words, ch.len, n_rec, W64_, ord_base, ord_stride, d_cnt_);
+        if (NW == 2 && insert_sm_)
+            k_chop_insert_sm2<<<blocks, INS_THREADS, 0, st_>>>(*reinterpret_cast<Table<2>*>(&tab_), *reinterpret_cast<KParams<2>*>(&kp_), ch.words, ch.len,
+                                                               n_rec, W64_, ord_base, ord_stride, d_cnt_);
+        else
+            k_chop_insert<NW><<<blocks, INS_THREADS, 0, st_>>>(tab_, kp_, ch.words, ch.len, n_rec, W64_, ord_base, ord_stride, d_cnt_);
         PG_CUDA(cudaGetLastError());
     }
     PG_CUDA(cudaEventRecord(ev_[3], st_));
@@ -502,6 +602,7 @@ EngineT<NW>::EngineT(const PgParams& p) : prm_(p) {
     // DRAM reads per k-mer instance with the default granularity, profiles/r01_insert_ncu.md)
     if (const char* g = getenv("PGB200_L2GRAN")) l2gran_mode_ = atoi(g);
     if (const char* g = getenv("PGB200_BUCKET")) bucket_mode_ = atoi(g);
+    if (const char* g = getenv("PGB200_INSERT_SM")) insert_sm_ = atoi(g);
     if (l2gran_mode_ == 1) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     kp_ = make_kparams<NW>(p.K);
     PG_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));

@@ -50,3 +50,44 @@ def exchange_round(eng, torch, dist, device):
         eng.apply_tuples(recv.data_ptr(), n)
     eng.exchange_clear()
     return n
+
+
+class PipelinedExchange:
+    """Same exchange, software-pipelined: the all-to-all of round i is in flight (NCCL stream, async) while the engine applies the
+    tuples received in round i-1 and buckets the chunk of round i+1 (the engine alternates between two tuple buffers)."""
+
+    def __init__(self, eng, torch, dist, device):
+        self.eng, self.torch, self.dist, self.device = eng, torch, dist, device
+        self.pending = None
+
+    def _drain(self):
+        if self.pending is None:
+            return 0
+        recv, n, work, send = self.pending
+        work.wait()
+        if recv.is_cuda:
+            self.torch.cuda.current_stream(recv.device).synchronize()
+        if n:
+            self.eng.apply_tuples(recv.data_ptr(), n)
+        self.pending = None
+        return n
+
+    def round(self):
+        torch, dist = self.torch, self.dist
+        ptr, ranges, tb = self.eng.exchange_buffer()
+        send_bytes = split_sizes(ranges, tb)
+        total = ranges[-1] * tb
+        send = torch.as_tensor(DeviceMemory(ptr, total), device=self.device) if total else torch.empty(0, dtype=torch.uint8, device=self.device)
+        sc = torch.tensor(send_bytes, dtype=torch.int64, device=self.device)
+        rc = torch.empty_like(sc)
+        dist.all_to_all_single(rc, sc)
+        recv_bytes = rc.tolist()
+        recv = torch.empty(sum(recv_bytes), dtype=torch.uint8, device=self.device)
+        work = dist.all_to_all_single(recv, send, output_split_sizes=recv_bytes, input_split_sizes=list(send_bytes), async_op=True)
+        self.eng.exchange_clear()
+        done = self._drain()                       # apply the previous round while this round's bytes move
+        self.pending = (recv, sum(recv_bytes) // tb, work, send)
+        return done
+
+    def finish(self):
+        return self._drain()
