@@ -79,7 +79,7 @@ public:
     cudaStream_t st_ = nullptr;
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     int W64_ = 0;   // packed words per read
-    int insert_sm_ = 1;     // PGB200_INSERT_SM=0: the lock-step k_chop_insert instead of the per-lane state machine (K <= 63)
+    int insert_sm_ = 0;     // PGB200_INSERT_SM=1: per-lane state-machine variant of the insert (K <= 63); measured slower, kept for the record
     int l2gran_mode_ = 0;   // PGB200_L2GRAN: 0 default, 1 = 32 B globally, 2 = 32 B only around k_chop_insert
 
     std::vector<ReadChunk> chunks_;
