@@ -39,20 +39,23 @@ struct CountSink {
 
 template <int NW>
 __global__ void __launch_bounds__(BK_THREADS) k_bucket_count(KParams<NW> kp, const u64* __restrict__ words, const u32* __restrict__ lens, u64 n_rec,
-                                                              int W64, u64 mask, int region_shift, int region_bits, int world, int NB, u32* tilecnt) {
+                                                              int W64, u64 mask, int region_shift, int region_bits, int world, int NB, u32* tilecnt,
+                                                              int rpt, u64 tile0) {
     extern __shared__ unsigned s_hist[];
     for (int b = threadIdx.x; b < NB; b += BK_THREADS) s_hist[b] = 0;
     __syncthreads();
-    u64 r = (u64)blockIdx.x * BK_THREADS + threadIdx.x;
-    if (r < n_rec) {
-        int L = (int)lens[r];
-        if (L >= kp.K + 1) {
-            CountSink<NW> sink{s_hist, mask, region_shift, region_bits, world};
-            chop_read(kp, words + r * (u64)W64, L, sink);
+    for (int q = 0; q < rpt; q++) {   // a tile = rpt * BK_THREADS consecutive reads of the chunk
+        u64 r = ((u64)blockIdx.x * rpt + q) * BK_THREADS + threadIdx.x;
+        if (r < n_rec) {
+            int L = (int)lens[r];
+            if (L >= kp.K + 1) {
+                CountSink<NW> sink{s_hist, mask, region_shift, region_bits, world};
+                chop_read(kp, words + r * (u64)W64, L, sink);
+            }
         }
     }
     __syncthreads();
-    u32* row = tilecnt + (u64)blockIdx.x * NB;
+    u32* row = tilecnt + (tile0 + blockIdx.x) * NB;
     for (int b = threadIdx.x; b < NB; b += BK_THREADS) row[b] = s_hist[b];
 }
 
@@ -94,17 +97,19 @@ struct ScatterSink {
 template <int NW>
 __global__ void __launch_bounds__(BK_THREADS) k_bucket_scatter(KParams<NW> kp, const u64* __restrict__ words, const u32* __restrict__ lens, u64 n_rec,
                                                                 int W64, u64 ord_base, u64 ord_stride, u64 mask, int region_shift, int region_bits,
-                                                                int world, int NB, const u32* tileoff, u64* tuples) {
+                                                                int world, int NB, const u32* tileoff, u64* tuples, int rpt, u64 tile0) {
     extern __shared__ unsigned s_cur[];
-    const u32* row = tileoff + (u64)blockIdx.x * NB;
+    const u32* row = tileoff + (tile0 + blockIdx.x) * NB;
     for (int b = threadIdx.x; b < NB; b += BK_THREADS) s_cur[b] = row[b];
     __syncthreads();
-    u64 r = (u64)blockIdx.x * BK_THREADS + threadIdx.x;
-    if (r < n_rec) {
-        int L = (int)lens[r];
-        if (L >= kp.K + 1) {
-            ScatterSink<NW> sink{s_cur, tuples, ord_base + r * ord_stride, mask, region_shift, region_bits, world};
-            chop_read(kp, words + r * (u64)W64, L, sink);
+    for (int q = 0; q < rpt; q++) {
+        u64 r = ((u64)blockIdx.x * rpt + q) * BK_THREADS + threadIdx.x;
+        if (r < n_rec) {
+            int L = (int)lens[r];
+            if (L >= kp.K + 1) {
+                ScatterSink<NW> sink{s_cur, tuples, ord_base + r * ord_stride, mask, region_shift, region_bits, world};
+                chop_read(kp, words + r * (u64)W64, L, sink);
+            }
         }
     }
 }
@@ -143,20 +148,26 @@ __global__ void __launch_bounds__(BK_THREADS) k_apply_tuples(Table<NW> tab, cons
 }
 
 template <int NW>
-void EngineT<NW>::bucket_chunk(const ReadChunk& ch) {
+void EngineT<NW>::bucket_chunk(const ReadChunk& ch) { bucket_chunks(&ch, 1, 8ull << 20, 1); }
+
+// Counting sort of the tuples of `n` chunks by (owner, table region of ~region_bytes).  rpt = reads per thread (tile size).
+template <int NW>
+void EngineT<NW>::bucket_chunks(const ReadChunk* chs, size_t n, u64 region_bytes, int rpt) {
     const int world = prm_.world > 1 ? prm_.world : 1;
-    // regions of ~8 MB of table (capped so that the per-block histogram fits in shared memory)
     int log2cap = 0;
     while ((1ull << log2cap) < cap_) log2cap++;
     u64 table_bytes = cap_ * sizeof(Slot<NW>);
     int rb = 0;
-    while ((table_bytes >> rb) > (8ull << 20) && rb < 12 && world * (2 << rb) <= 8192) rb++;
+    while ((table_bytes >> rb) > region_bytes && rb < 12 && world * (2 << rb) <= 8192) rb++;
     if (rb > log2cap) rb = log2cap;
     region_bits_ = rb;
     const int region_shift = log2cap - rb;
     const int NB = world << rb;
     n_buckets_ = NB;
-    const u64 n_tiles = (ch.n_rec + BK_THREADS - 1) / BK_THREADS;
+    const u64 tile_reads = (u64)BK_THREADS * rpt;
+    std::vector<u64> tile0(n + 1, 0);
+    for (size_t c = 0; c < n; c++) tile0[c + 1] = tile0[c] + (chs[c].n_rec + tile_reads - 1) / tile_reads;
+    const u64 n_tiles = tile0[n];
     const u64 cells = n_tiles * (u64)NB;
     tilecnt_buf_.ensure(cells * sizeof(u32));
     tileoff_buf_.ensure(cells * sizeof(u32));
@@ -168,8 +179,11 @@ void EngineT<NW>::bucket_chunk(const ReadChunk& ch) {
         cudaFuncSetAttribute(k_bucket_scatter<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         attr_set = true;
     }
-    k_bucket_count<NW><<<(unsigned)n_tiles, BK_THREADS, smem, st_>>>(kp_, ch.words, ch.len, ch.n_rec, W64_, tab_.mask, region_shift, rb, world, NB,
-                                                                     tilecnt_buf_.template as<u32>());
+    for (size_t c = 0; c < n; c++) {
+        if (!chs[c].n_rec) continue;
+        k_bucket_count<NW><<<(unsigned)(tile0[c + 1] - tile0[c]), BK_THREADS, smem, st_>>>(kp_, chs[c].words, chs[c].len, chs[c].n_rec, W64_, tab_.mask, region_shift,
+                                                                                          rb, world, NB, tilecnt_buf_.template as<u32>(), rpt, tile0[c]);
+    }
     PG_CUDA(cudaGetLastError());
     device_scan(TileCntIn{tilecnt_buf_.template as<u32>(), n_tiles, NB}, TileOffOut{tileoff_buf_.template as<u32>(), n_tiles, NB}, cells,
                 scan_buf_.template as<u64>(), d_cnt_ + C_MISC1, st_);
@@ -178,16 +192,39 @@ void EngineT<NW>::bucket_chunk(const ReadChunk& ch) {
     PG_CUDA(cudaMemcpyAsync(first_row.data(), tileoff_buf_.p, NB * sizeof(u32), cudaMemcpyDeviceToHost, st_));
     read_counters();
     n_tuples_ = h_cnt_[C_MISC1];
-    if (n_tuples_ >= 0xFFFFFFFFull) throw std::runtime_error("pgb200: more than 2^32 k-mer instances in one chunk; feed smaller chunks");
+    if (n_tuples_ >= 0xFFFFFFFFull) throw std::runtime_error("pgb200: more than 2^32 k-mer instances in one batch; use a smaller batch");
     owner_start_.assign(world + 1, n_tuples_);
     for (int o = 0; o < world; o++) owner_start_[o] = first_row[(size_t)o << rb];
     tuple_flip_ ^= 1;
     tuple_buf().ensure((n_tuples_ + 1) * TupleW<NW>::value * sizeof(u64));
-    k_bucket_scatter<NW><<<(unsigned)n_tiles, BK_THREADS, smem, st_>>>(kp_, ch.words, ch.len, ch.n_rec, W64_, ch.ord_base, ch.ord_stride, tab_.mask,
-                                                                       region_shift, rb, world, NB, tileoff_buf_.template as<u32>(),
-                                                                       tuple_buf().template as<u64>());
+    for (size_t c = 0; c < n; c++) {
+        if (!chs[c].n_rec) continue;
+        k_bucket_scatter<NW><<<(unsigned)(tile0[c + 1] - tile0[c]), BK_THREADS, smem, st_>>>(kp_, chs[c].words, chs[c].len, chs[c].n_rec, W64_, chs[c].ord_base,
+                                                                                            chs[c].ord_stride, tab_.mask, region_shift, rb, world, NB,
+                                                                                            tileoff_buf_.template as<u32>(), tuple_buf().template as<u64>(), rpt, tile0[c]);
+    }
     PG_CUDA(cudaGetLastError());
-    p1_.launches += 5;
+    p1_.launches += 3 + 2 * n;
+}
+
+// Batch mode (single GPU): every chunk fed since the last flush is bucketed by 32 MB table region in ONE counting sort and applied
+// region by region.  The whole table streams through L2 once per batch instead of being hit at random once per instance; the
+// price is 32 B written + read per instance for the tuple buffer.
+template <int NW>
+void EngineT<NW>::flush_batch() {
+    if (pending_first_ >= chunks_.size()) return;
+    settle_timing();
+    read_counters();
+    ensure_table_bound(h_cnt_[C_DISTINCT], pending_bound_);
+    PG_CUDA(cudaEventRecord(ev_[0], st_));
+    PG_CUDA(cudaEventRecord(ev_[1], st_));
+    PG_CUDA(cudaEventRecord(ev_[2], st_));
+    bucket_chunks(chunks_.data() + pending_first_, chunks_.size() - pending_first_, 32ull << 20, 4);
+    apply_tuples(tuple_buf().template as<u64>(), n_tuples_);
+    PG_CUDA(cudaEventRecord(ev_[3], st_));
+    timing_pending_ = true;
+    pending_first_ = chunks_.size();
+    pending_bound_ = 0;
 }
 
 template <int NW>
@@ -201,6 +238,10 @@ void EngineT<NW>::apply_tuples(const u64* tuples, u64 n) {
 }
 
 template void EngineT<2>::bucket_chunk(const ReadChunk&);
+template void EngineT<2>::bucket_chunks(const ReadChunk*, size_t, u64, int);
+template void EngineT<4>::bucket_chunks(const ReadChunk*, size_t, u64, int);
+template void EngineT<2>::flush_batch();
+template void EngineT<4>::flush_batch();
 template void EngineT<4>::bucket_chunk(const ReadChunk&);
 template void EngineT<2>::apply_tuples(const u64*, u64);
 template void EngineT<4>::apply_tuples(const u64*, u64);

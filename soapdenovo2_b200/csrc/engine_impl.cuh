@@ -80,6 +80,7 @@ public:
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     int W64_ = 0;   // packed words per read
     int insert_sm_ = 0;     // PGB200_INSERT_SM=1: per-lane state-machine variant of the insert (K <= 63); measured slower, kept for the record
+    int dbg_insert_ = 0;    // PGB200_DBG_INSERT: cost-decomposition variants of k_chop_insert (profiling only)
     int l2gran_mode_ = 0;   // PGB200_L2GRAN: 0 default, 1 = 32 B globally, 2 = 32 B only around k_chop_insert
 
     std::vector<ReadChunk> chunks_;
@@ -120,6 +121,12 @@ public:
     int n_buckets_ = 0, region_bits_ = 0;
     std::vector<u64> owner_start_;   // [world + 1] tuple offsets of each owner's range in tuple_buf_
     void bucket_chunk(const ReadChunk& ch);
+    void bucket_chunks(const ReadChunk* chs, size_t n, u64 region_bytes, int rpt);
+    // batch mode (PGB200_BATCH_GB > 0): inserts are deferred and done region-sorted over many chunks at once
+    double batch_gb_ = 0;
+    size_t pending_first_ = 0;   // chunks_[pending_first_..) are decoded but not inserted yet
+    u64 pending_bound_ = 0;      // upper bound of their k-mer instances
+    void flush_batch();
     void apply_tuples(const u64* tuples, u64 n);
 public:
     // multi-GPU exchange surface (C-ABI: pgb200_exchange_*)

@@ -159,15 +159,22 @@ struct InsertSink {
     const Table<NW>& tab;
     u64 rank_base;
     unsigned& my_new;
+    int dbg;   // 0 = the real thing; 1..4 = cost-decomposition variants for profiling (PGB200_DBG_INSERT, results are garbage)
     __device__ __forceinline__ void operator()(const Kmer<NW>& canon, unsigned left, unsigned right, int j) {
-        my_new += table_insert(tab, canon, left, right, rank_base | (u64)j);
+        if (dbg == 0) { my_new += table_insert(tab, canon, left, right, rank_base | (u64)j); return; }
+        u64 idx = table_hash(canon) & tab.mask;
+        if (dbg == 1) { my_new += (unsigned)(idx & 1) + left + right; return; }                               // ALU only
+        Slot<NW>* s = tab.slots + idx;
+        if (dbg == 2) { U128 v = ldcg128(s->key); my_new += (v.a == canon.w[0]); return; }                      // + one probe load
+        if (dbg == 3) { atomicAdd(&s->payload, 0ull); return; }                                                // blind RED, no load
+        if (dbg == 4) { U128 v = ldcg128(s->key); u64 o = atomicAdd(&s->payload, (u64)(v.a & 0)); my_new += (unsigned)(o & 1); return; }   // load -> dependent returning atomic
     }
 };
 
 template <int NW>
 __global__ void __launch_bounds__(INS_THREADS, INS_MIN_BLOCKS) k_chop_insert(Table<NW> tab, KParams<NW> kp, const u64* __restrict__ words,
                                                              const u32* __restrict__ lens, u64 n_rec, int W64, u64 ord_base, u64 ord_stride,
-                                                             u64* counters) {
+                                                             u64* counters, int dbg) {
     __shared__ unsigned s_new;
     if (threadIdx.x == 0) s_new = 0;
     __syncthreads();
@@ -175,7 +182,7 @@ __global__ void __launch_bounds__(INS_THREADS, INS_MIN_BLOCKS) k_chop_insert(Tab
     for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += (u64)gridDim.x * blockDim.x) {
         const int L = (int)lens[r];
         if (L < kp.K + 1) continue;
-        InsertSink<NW> sink{tab, (ord_base + r * ord_stride) << 16, my_new};
+        InsertSink<NW> sink{tab, (ord_base + r * ord_stride) << 16, my_new, dbg};
         chop_read(kp, words + r * (u64)W64, L, sink);
     }
     if (my_new) atomicAdd(&s_new, my_new);
@@ -470,6 +477,10 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     PG_CUDA(cudaEventRecord(ev_[2], st_));
     if (prm_.world > 1) {
         bucket_chunk(ch);                       // tuples stay in the exchange buffer: caller runs the all-to-all
+    } else if (batch_gb_ > 0) {
+        int per_read = maxlen - prm_.K + 1;
+        pending_bound_ += per_read > 0 ? n_rec * (u64)per_read : 0;
+        if ((double)pending_bound_ * 32.0 >= batch_gb_ * 1e9 || pending_bound_ >= 0xF0000000ull) flush_batch();
     } else if (bucket_mode_) {
         bucket_chunk(ch);
         apply_tuples(tuple_buf().template as<u64>(), n_tuples_);
@@ -479,7 +490,7 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
             k_chop_insert_sm2<<<blocks, INS_THREADS, 0, st_>>>(*reinterpret_cast<Table<2>*>(&tab_), *reinterpret_cast<KParams<2>*>(&kp_), ch.words, ch.len,
                                                                n_rec, W64_, ord_base, ord_stride, d_cnt_);
         else
-            k_chop_insert<NW><<<blocks, INS_THREADS, 0, st_>>>(tab_, kp_, ch.words, ch.len, n_rec, W64_, ord_base, ord_stride, d_cnt_);
+            k_chop_insert<NW><<<blocks, INS_THREADS, 0, st_>>>(tab_, kp_, ch.words, ch.len, n_rec, W64_, ord_base, ord_stride, d_cnt_, dbg_insert_);
         PG_CUDA(cudaGetLastError());
     }
     PG_CUDA(cudaEventRecord(ev_[3], st_));
@@ -508,6 +519,7 @@ void EngineT<NW>::settle_timing() {
 
 template <int NW>
 void EngineT<NW>::finish_pass1(Pass1Stats* st) {
+    flush_batch();
     settle_timing();
     read_counters();
     p1_.records = total_records_;
@@ -525,6 +537,8 @@ void EngineT<NW>::reset_pass1() {
     settle_timing();
     sync();
     chunks_.clear();
+    pending_first_ = 0;
+    pending_bound_ = 0;
     // keep the first arena block for the next pass, release the rest
     while (arena_.size() > 1) { cudaFree(arena_.back().first); arena_.pop_back(); }
     arena_used_ = 0;
@@ -578,6 +592,7 @@ __global__ void __launch_bounds__(256) k_sweep(Table<NW> tab, int D, u64* hist, 
 template <int NW>
 void EngineT<NW>::sweeps(SweepStats* st) {
     double t0 = host_now();
+    flush_batch();
     DevBuf hist;
     hist.alloc(256 * sizeof(u64));
     PG_CUDA(cudaMemsetAsync(hist.p, 0, 256 * sizeof(u64), st_));
@@ -603,6 +618,8 @@ EngineT<NW>::EngineT(const PgParams& p) : prm_(p) {
     if (const char* g = getenv("PGB200_L2GRAN")) l2gran_mode_ = atoi(g);
     if (const char* g = getenv("PGB200_BUCKET")) bucket_mode_ = atoi(g);
     if (const char* g = getenv("PGB200_INSERT_SM")) insert_sm_ = atoi(g);
+    if (const char* g = getenv("PGB200_DBG_INSERT")) dbg_insert_ = atoi(g);
+    if (const char* g = getenv("PGB200_BATCH_GB")) batch_gb_ = atof(g);
     if (l2gran_mode_ == 1) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     kp_ = make_kparams<NW>(p.K);
     PG_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
