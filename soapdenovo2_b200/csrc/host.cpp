@@ -18,6 +18,7 @@
 #include <ctime>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 #include <getopt.h>
 #include <unistd.h>
@@ -142,13 +143,8 @@ extern "C" int pgb200_remove_tips(pgb200_engine* e, pgb200_graph_stats* st) {
     if (st) { st->single_tips = t.single_tips; st->minor_tips = t.minor_tips; }
     PG_CATCH
 }
-extern "C" int pgb200_kmer2edges(pgb200_engine* e, const char* prefix, pgb200_graph_stats* st) {
-    PG_TRY
-    EdgeStats es;
-    std::string text;
-    e->e->build_edges(&es, &text);
-    // gzopen(name,"w") + gzwrite: same zlib, same default level => the same byte stream as the reference's gzprintf calls
-    std::string name = std::string(prefix) + ".edge.gz";
+// gzopen(name,"w") + gzwrite: same zlib, same default level => the same byte stream as the reference's gzprintf calls
+static void write_edge_gz(const std::string& name, const std::string& text) {
     gzFile gz = gzopen(name.c_str(), "w");
     if (!gz) throw std::runtime_error("Cannot open " + name);
     size_t off = 0;
@@ -158,6 +154,14 @@ extern "C" int pgb200_kmer2edges(pgb200_engine* e, const char* prefix, pgb200_gr
         off += n;
     }
     gzclose(gz);
+}
+
+extern "C" int pgb200_kmer2edges(pgb200_engine* e, const char* prefix, pgb200_graph_stats* st) {
+    PG_TRY
+    EdgeStats es;
+    std::string text;
+    e->e->build_edges(&es, &text);
+    write_edge_gz(std::string(prefix) + ".edge.gz", text);
     fprintf(stderr, "%llu (%llu) edge(s) and %llu extra node(s) constructed.\n", (unsigned long long)es.num_ed, (unsigned long long)es.edges,
             (unsigned long long)es.extra_nodes);
     if (st) { st->num_ed = es.num_ed; st->edges = es.edges; st->extra_nodes = es.extra_nodes; }
@@ -431,12 +435,25 @@ extern "C" int pgb200_pregraph_main(int argc, char** argv, int flavour127) {
     fprintf(stderr, "Time spent on removing tips: %ds.\n\n", (int)(now_s() - t0));
     // ---- edges (kmer2edges)
     t0 = now_s();
-    if (pgb200_kmer2edges(eng, prefix.c_str(), &gs)) die("edges");
+    // The deflate of the edge text is sequential host work (it has to be: the bytes must equal the reference's gz stream);
+    // it runs on a host thread while the GPU does pass 2.
+    std::string edge_text, gz_error;
+    std::thread gz_thread;
+    try {
+        EdgeStats es;
+        eng->e->build_edges(&es, &edge_text);
+        fprintf(stderr, "%llu (%llu) edge(s) and %llu extra node(s) constructed.\n", (unsigned long long)es.num_ed, (unsigned long long)es.edges,
+                (unsigned long long)es.extra_nodes);
+        gs.num_ed = es.num_ed; gs.edges = es.edges; gs.extra_nodes = es.extra_nodes;
+        gz_thread = std::thread([&]() { try { write_edge_gz(prefix + ".edge.gz", edge_text); } catch (const std::exception& ex) { gz_error = ex.what(); } });
+    } catch (const std::exception& ex) { fprintf(stderr, "pgb200: edges failed: %s\n", ex.what()); exit(-1); }
     fprintf(stderr, "Time spent on constructing edges: %ds.\n\n", (int)(now_s() - t0));
     // ---- pass 2 (prlRead2edge)
     t0 = now_s();
-    if (pgb200_read2edge(eng, prefix.c_str(), &gs)) die("pass 2");
+    if (pgb200_read2edge(eng, prefix.c_str(), &gs)) { if (gz_thread.joinable()) gz_thread.join(); die("pass 2"); }
     fprintf(stderr, "Time spent on aligning reads: %ds.\n\n", (int)(now_s() - t0));
+    gz_thread.join();
+    if (!gz_error.empty()) { fprintf(stderr, "%s\n", gz_error.c_str()); exit(-1); }
     if (pgb200_output_vertex(eng, prefix.c_str(), &gs)) die("vertex output");
     pgb200_destroy(eng);
     fprintf(stderr, "Overall time spent on constructing pre-graph: %dm.\n\n", (int)(now_s() - t_all) / 60);
