@@ -134,8 +134,8 @@ __global__ void __launch_bounds__(BK_THREADS) k_apply_tuples(Table<NW> tab, cons
     // order, so the blocks resident at any moment cover one contiguous window of the region-sorted tuples (a persistent
     // grid drifts apart and the window -- hence the table working set -- grows without bound; measured: 180 B of DRAM reads
     // per tuple with the persistent variant).
-    u64 i = (u64)blockIdx.x * BK_THREADS + threadIdx.x;
-    if (i < n) {
+    // (a persistent grid was also measured for the exchange path, where order does not matter: 139 ms vs 78 ms per 8.8e8 tuples)
+    for (u64 i = (u64)blockIdx.x * BK_THREADS + threadIdx.x; i < n; i += (u64)gridDim.x * BK_THREADS) {
         const u64* t = tuples + i * TupleW<NW>::value;
         U256 a;
         asm volatile("ld.global.cs.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a.a), "=l"(a.b), "=l"(a.c), "=l"(a.d) : "l"(t));
