@@ -38,4 +38,30 @@ __device__ __forceinline__ void chop_read(const KParams<NW>& kp, const u64* __re
 // tuple meta word: ordinal << 22 | position << 6 | left << 3 | right ; first-occurrence rank == meta >> 6
 PG_HD u64 tuple_meta(u64 ord, int j, unsigned left, unsigned right) { return (ord << 22) | ((u64)j << 6) | (left << 3) | right; }
 
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------- TMA staging of a tile of packed reads
+// A block's 256 reads are one contiguous run of the read store (256 x W64 x 8 B, e.g. 10 KB at 150 bp): one elected thread
+// arms an mbarrier with the byte count and issues a single bulk tensor-less TMA copy (cp.async.bulk -> SASS UBLKCP.S.G);
+// every thread then rolls its read out of shared memory instead of issuing strided 8-byte global loads.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, unsigned parity) {
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(
+                     smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+#endif
+
 }   // namespace pgb

@@ -174,16 +174,38 @@ struct InsertSink {
 template <int NW>
 __global__ void __launch_bounds__(INS_THREADS, INS_MIN_BLOCKS) k_chop_insert(Table<NW> tab, KParams<NW> kp, const u64* __restrict__ words,
                                                              const u32* __restrict__ lens, u64 n_rec, int W64, u64 ord_base, u64 ord_stride,
-                                                             u64* counters, int dbg) {
+                                                             u64* counters, int dbg, int use_tma) {
+    extern __shared__ __align__(128) u64 s_words[];   // [INS_THREADS][W64] when use_tma
+    __shared__ __align__(8) u64 s_bar;
     __shared__ unsigned s_new;
-    if (threadIdx.x == 0) s_new = 0;
+    if (threadIdx.x == 0) { s_new = 0; if (use_tma) mbar_init(&s_bar, 1); }
     __syncthreads();
     unsigned my_new = 0;
-    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += (u64)gridDim.x * blockDim.x) {
-        const int L = (int)lens[r];
-        if (L < kp.K + 1) continue;
-        InsertSink<NW> sink{tab, (ord_base + r * ord_stride) << 16, my_new, dbg};
-        chop_read(kp, words + r * (u64)W64, L, sink);
+    const u64 n_tiles = (n_rec + INS_THREADS - 1) / INS_THREADS;
+    unsigned parity = 0;
+    for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const u64 r0 = tile * INS_THREADS;
+        const u64 r = r0 + threadIdx.x;
+        const u64* wp = words + r * (u64)W64;
+        if (use_tma) {
+            u64 cnt = n_rec - r0 < (u64)INS_THREADS ? n_rec - r0 : (u64)INS_THREADS;
+            unsigned bytes = (unsigned)((cnt * (u64)W64 * 8 + 15) & ~15ull);   // the arena pads every allocation to 256 B
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&s_bar, bytes);
+                tma_bulk_g2s(s_words, words + r0 * (u64)W64, bytes, &s_bar);
+            }
+            mbar_wait(&s_bar, parity);
+            parity ^= 1;
+            wp = s_words + (u64)threadIdx.x * W64;
+        }
+        if (r < n_rec) {
+            const int L = (int)lens[r];
+            if (L >= kp.K + 1) {
+                InsertSink<NW> sink{tab, (ord_base + r * ord_stride) << 16, my_new, dbg};
+                chop_read(kp, wp, L, sink);
+            }
+        }
+        if (use_tma) __syncthreads();   // the tile buffer is reused by the next bulk copy
     }
     if (my_new) atomicAdd(&s_new, my_new);
     __syncthreads();
@@ -490,7 +512,13 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
             k_chop_insert_sm2<<<blocks, INS_THREADS, 0, st_>>>(*reinterpret_cast<Table<2>*>(&tab_), *reinterpret_cast<KParams<2>*>(&kp_), ch.words, ch.len,
                                                                n_rec, W64_, ord_base, ord_stride, d_cnt_);
         else
-            k_chop_insert<NW><<<blocks, INS_THREADS, 0, st_>>>(tab_, kp_, ch.words, ch.len, n_rec, W64_, ord_base, ord_stride, d_cnt_, dbg_insert_);
+        {
+            size_t smem = (size_t)INS_THREADS * W64_ * sizeof(u64);
+            int use_tma = smem <= 96 * 1024 && !getenv("PGB200_NO_TMA");
+            if (use_tma && smem > 48 * 1024) cudaFuncSetAttribute(k_chop_insert<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_chop_insert<NW><<<blocks, INS_THREADS, use_tma ? smem : 0, st_>>>(tab_, kp_, ch.words, ch.len, n_rec, W64_, ord_base, ord_stride, d_cnt_,
+                                                                              dbg_insert_, use_tma);
+        }
         PG_CUDA(cudaGetLastError());
     }
     PG_CUDA(cudaEventRecord(ev_[3], st_));

@@ -13,6 +13,7 @@
 #include "engine_impl.cuh"
 #include "scan.cuh"
 #include "patch.cuh"
+#include "chop.cuh"
 #include <algorithm>
 
 namespace pgb {
@@ -47,14 +48,31 @@ template <int NW>
 __global__ void __launch_bounds__(128) k_pass2(Table<NW> tab, KParams<NW> kp, const u64* __restrict__ words, const u32* __restrict__ lens, u64 n_rec,
                                                int W64, u64 ord_base, u64 ord_stride, int stride, u32* pathbuf, u32* reclen, int repsTie,
                                                const PatchSlot<NW>* patch, u64 pmask, bool quirk128, ArcSlot* arcs, u64 amask, u32* marker,
-                                               u64* counters, u64* err) {
+                                               u64* counters, u64* err, int use_tma) {
+    extern __shared__ __align__(128) u64 s_words[];   // TMA-staged tile of packed reads (see chop.cuh)
+    __shared__ __align__(8) u64 s_bar;
+    if (threadIdx.x == 0 && use_tma) mbar_init(&s_bar, 1);
+    __syncthreads();
     const int K = kp.K;
     unsigned deleted_reads = 0;
-    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += (u64)gridDim.x * blockDim.x) {
+    unsigned parity = 0;
+    const u64 n_tiles = (n_rec + blockDim.x - 1) / blockDim.x;
+    for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const u64 r0 = tile * blockDim.x;
+        const u64 r = r0 + threadIdx.x;
+        if (use_tma) {
+            if (tile != blockIdx.x) __syncthreads();   // previous tile fully consumed
+            u64 cnt = n_rec - r0 < (u64)blockDim.x ? n_rec - r0 : (u64)blockDim.x;
+            unsigned bytes = (unsigned)((cnt * (u64)W64 * 8 + 15) & ~15ull);
+            if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, bytes); tma_bulk_g2s(s_words, words + r0 * (u64)W64, bytes, &s_bar); }
+            mbar_wait(&s_bar, parity);
+            parity ^= 1;
+        }
+        if (r >= n_rec) continue;
         const int L = (int)lens[r];
         if (L < K + 1) continue;                       // skipped exactly like pass 1 (prlRead2path.c:1012 etc.)
         const u64 ord = ord_base + r * ord_stride;
-        const u64* wp = words + r * (u64)W64;
+        const u64* wp = use_tma ? s_words + (u64)threadIdx.x * W64 : words + r * (u64)W64;
         u32* mix = pathbuf + r * (u64)stride;
         const int n = L - K + 1;
         Kmer<NW> fwd = kzero<NW>(), rc = kzero<NW>(), prevK = kzero<NW>();
@@ -192,9 +210,11 @@ void EngineT<NW>::pass2(Pass2Stats* st, std::string* prearc_text, std::string* p
         if (prm_.repsTie) { pathbufs[ci].alloc(c.n_rec * (u64)stride * sizeof(u32)); pb = pathbufs[ci].template as<u32>(); }
         else pb = shared_path.template as<u32>();
         unsigned blocks = (unsigned)std::min<u64>((c.n_rec + 127) / 128, 148ull * 32);
-        k_pass2<NW><<<blocks, 128, 0, st_>>>(tab_, kp_, c.words, c.len, c.n_rec, W64_, c.ord_base, c.ord_stride, stride, pb,
+        size_t smem = (size_t)128 * W64_ * sizeof(u64);
+        int use_tma = smem <= 48 * 1024 && !getenv("PGB200_NO_TMA");
+        k_pass2<NW><<<blocks, 128, use_tma ? smem : 0, st_>>>(tab_, kp_, c.words, c.len, c.n_rec, W64_, c.ord_base, c.ord_stride, stride, pb,
                                              reclenb.template as<u32>(), prm_.repsTie, patch_buf_.template as<PatchSlot<NW>>(), patch_mask_,
-                                             quirk128, arcs, acap - 1, markb.template as<u32>(), d_cnt_, errb.template as<u64>());
+                                             quirk128, arcs, acap - 1, markb.template as<u32>(), d_cnt_, errb.template as<u64>(), use_tma);
         PG_CUDA(cudaGetLastError());
     }
     u64 herr[2];
