@@ -564,8 +564,27 @@ static void vertices(void) { /* output_vertex output_pregraph.c:50-86 */
     fclose(fb);
 }
 
+/* -V : print known-answer vectors of the restated primitives (compared with tests/golden/kats.json by tests/test_kats.py) */
+static void self_kats(void) {
+    const char *s = "ACGTTGCATGCAAGCTTAGCTAGGATCCATCGATCGGGCTATATCGCGATTAGCCATGCAGGT";
+    K = 63; crc_init(); MASKK = kmask(K);
+    Kmer f = kzero(), r;
+    for (const char *p = s; *p; p++) f = knext(f, (*p & 6) >> 1);
+    r = krc(f, K);
+    printf("hash_zero 0x%llx\n", (unsigned long long)hash_kmer(kzero()));
+    printf("kmer63_fwd 0x%llx 0x%llx\n", (unsigned long long)f.w[NW - 2], (unsigned long long)f.w[NW - 1]);
+    printf("kmer63_rc 0x%llx 0x%llx\n", (unsigned long long)r.w[NW - 2], (unsigned long long)r.w[NW - 1]);
+    printf("kmer63_smaller_fwd_rc %d\n", kcmp(f, r) < 0);
+    printf("kmer63_hash_fwd 0x%llx\n", (unsigned long long)(hash_kmer(f) & 0xffffffffULL));
+    printf("kmer63_hash_rc 0x%llx\n", (unsigned long long)(hash_kmer(r) & 0xffffffffULL));
+    Set *a = set_new(1024, 0.77f, 0), *b = set_new(3 * 0xFFFFFFULL, 0.77f, 1);
+    printf("init_kmerset_0 %llu %llu\n", (unsigned long long)a->size, (unsigned long long)a->max);
+    printf("init_kmerset_1 %llu %llu\n", (unsigned long long)b->size, (unsigned long long)b->max);
+}
+
 int main(int argc, char **argv) {
     const char *cfg = NULL, *tdump = NULL; int only1 = 0, c; K = 23;
+    if (argc > 1 && !strcmp(argv[1], "-V")) { self_kats(); return 0; }
     if (argc > 1 && !strcmp(argv[1], "pregraph")) { argv++; argc--; }
     while ((c = getopt(argc, argv, "a:s:o:K:p:d:RT:1")) != -1) switch (c) {
         case 's': cfg = optarg; break; case 'o': prefix = optarg; break; case 'K': K = atoi(optarg); break;

@@ -44,3 +44,17 @@ def test_crc_identity_with_zlib():
 def test_base_codes():
     for ch, code in GOLD["base2int"].items():
         assert (ord(ch) & 6) >> 1 == code and (ord(ch.lower()) & 6) >> 1 == code
+
+
+def test_oracle_model_matches_reference_kats():
+    """The CPU restatement's own primitives against the same golden vectors (both builds)."""
+    util.build_oracle()
+    for exe in (util.MODEL63, util.MODEL127):
+        out = subprocess.run([exe, "-V"], check=True, capture_output=True, text=True).stdout
+        got = {l.split()[0]: l.split()[1:] for l in out.splitlines()}
+        assert got["hash_zero"] == [GOLD["hash_zero_63"]]
+        assert got["kmer63_fwd"] == GOLD["kmer63_fwd"] and got["kmer63_rc"] == GOLD["kmer63_rc"]
+        assert int(got["kmer63_smaller_fwd_rc"][0]) == GOLD["kmer63_smaller_fwd_rc"]
+        assert got["kmer63_hash_fwd"] == [GOLD["kmer63_hash_fwd"]] and got["kmer63_hash_rc"] == [GOLD["kmer63_hash_rc"]]
+        for i, (req, lf, size, mx) in enumerate(GOLD["init_kmerset"]):
+            assert [int(x) for x in got[f"init_kmerset_{i}"]] == [size, mx]
