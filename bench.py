@@ -245,7 +245,7 @@ def main():
                 n = min(chunk, total - off)
                 work.append((base + off, n, (off // REC_BYTES) * 2 + mate))
                 off += n
-        pipe = pdist.PipelinedExchange(eng, torch, dist, dev) if world > 1 else None
+        pipe = xchg if world > 1 else None
         for r0 in range(0, len(work), world):
             i = r0 + rank
             if i < len(work):
@@ -258,6 +258,12 @@ def main():
         st = eng.finish_pass1()
         hist, lin, rem = eng.sweeps()   # D2H of the histogram + counters: the step's result
         return st, hist
+
+    xchg = None
+    if world > 1:
+        mode = os.environ.get("PGB200_XCHG", "fused")
+        xchg = (pdist.FusedExchange(eng, torch, dist, dev, cap_tuples=int(2.2 * args.chunk_reads * (RD_LEN - K + 1)))
+                if mode == "fused" else pdist.PipelinedExchange(eng, torch, dist, dev))
 
     def timed(bufs, on_device, steps, warmup):
         for _ in range(warmup):
@@ -344,7 +350,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
         "config": {"workload": workload, "reads": 2 * n_pairs, "kmer_instances": int(instances), "distinct_kmers": int(distinct),
-                   "instances_per_s": instances / (ms_step / 1e3), "table_slots_per_gpu": int(st.table_slots), "parallelism": f"k-mer space sharded over {world} GPU(s) by owner hash" + (", bucketed NCCL all-to-all per chunk round" if world > 1 else ""),
+                   "instances_per_s": instances / (ms_step / 1e3), "table_slots_per_gpu": int(st.table_slots), "parallelism": f"k-mer space sharded over {world} GPU(s) by owner hash" + (", tuples stored straight into the owner GPU over NVLink by the bucketing kernel (PGB200_XCHG=nccl: NCCL all-to-all)" if world > 1 else ""),
                    "l2_policy": "inputs (6.3 GB text, 17 GB table) are far larger than the 126 MB L2; the table is cleared every step"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_b}))
 

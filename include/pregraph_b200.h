@@ -80,6 +80,18 @@ uint64_t pgb200_last_chunk_records(pgb200_engine *e);
 const void *pgb200_exchange_buffer(pgb200_engine *e, uint64_t *ranges, int *tuple_bytes);
 int pgb200_exchange_clear(pgb200_engine *e);
 int pgb200_apply_tuples(pgb200_engine *e, const void *dev_tuples, uint64_t n_tuples);
+
+/* Fused exchange (no library collective on the data path): every rank owns two receive buffers; the other ranks map them with
+ * CUDA IPC and the scatter kernel stores each tuple STRAIGHT into its owner's buffer over NVLink while it is still chopping the
+ * next reads.  Protocol per round: feed_text (decode + count) -> xchg_counts -> [callers all-gather the world x world count
+ * matrix: 8 bytes per pair] -> xchg_scatter(buf, base) with base[o] = sum of the counts of lower ranks for owner o ->
+ * [barrier] -> xchg_apply(buf, sum of counts for me).  handle64 = the 64-byte cudaIpcMemHandle_t of buffer `buf`.          */
+int pgb200_xchg_setup(pgb200_engine *e, uint64_t cap_tuples);
+int pgb200_xchg_export(pgb200_engine *e, int buf, void *handle64);
+int pgb200_xchg_import(pgb200_engine *e, int peer, int buf, const void *handle64);
+int pgb200_xchg_counts(pgb200_engine *e, uint64_t *counts);
+int pgb200_xchg_scatter(pgb200_engine *e, int buf, const uint64_t *base);
+int pgb200_xchg_apply(pgb200_engine *e, int buf, uint64_t n_tuples);
 int pgb200_finish_pass1(pgb200_engine *e, pgb200_pass1_stats *st);
 int pgb200_reset_pass1(pgb200_engine *e);
 /* delow (-d) + mark linear + coverage histogram: hist[c] = number of k-mers with coverage c (the .kmerFreq lines are hist[1..255]) */

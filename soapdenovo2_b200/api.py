@@ -15,7 +15,8 @@ BIN127 = os.path.join(_HERE, "bin", "pregraph-b200-127mer")
 
 EXPORTS = [
     "pgb200_last_error", "pgb200_default_params", "pgb200_create", "pgb200_destroy", "pgb200_host_alloc", "pgb200_host_free",
-    "pgb200_feed_text", "pgb200_last_chunk_records", "pgb200_exchange_buffer", "pgb200_exchange_clear", "pgb200_apply_tuples", "pgb200_finish_pass1", "pgb200_reset_pass1", "pgb200_sweeps",
+    "pgb200_feed_text", "pgb200_last_chunk_records", "pgb200_exchange_buffer", "pgb200_exchange_clear", "pgb200_apply_tuples",
+    "pgb200_xchg_setup", "pgb200_xchg_export", "pgb200_xchg_import", "pgb200_xchg_counts", "pgb200_xchg_scatter", "pgb200_xchg_apply", "pgb200_finish_pass1", "pgb200_reset_pass1", "pgb200_sweeps",
     "pgb200_build_layout", "pgb200_node_count", "pgb200_dump_nodes", "pgb200_remove_tips", "pgb200_kmer2edges",
     "pgb200_read2edge", "pgb200_output_vertex", "pgb200_pregraph_main", "call_pregraph",
 ]
@@ -61,6 +62,12 @@ def load():
     lib.pgb200_exchange_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
     lib.pgb200_exchange_clear.argtypes = [C.c_void_p]
     lib.pgb200_apply_tuples.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.pgb200_xchg_setup.argtypes = [C.c_void_p, C.c_uint64]
+    lib.pgb200_xchg_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.pgb200_xchg_import.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.pgb200_xchg_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.pgb200_xchg_scatter.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
+    lib.pgb200_xchg_apply.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
     lib.pgb200_finish_pass1.argtypes = [C.c_void_p, C.POINTER(Pass1Stats)]
     lib.pgb200_reset_pass1.argtypes = [C.c_void_p]
     lib.pgb200_sweeps.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -133,6 +140,32 @@ class PregraphEngine:
 
     def apply_tuples(self, dev_ptr, n_tuples):
         self._ck(self.lib.pgb200_apply_tuples(self.h, C.c_void_p(int(dev_ptr)), n_tuples))
+
+    # ---- fused exchange (peer stores over NVLink): see include/pregraph_b200.h
+    def xchg_setup(self, cap_tuples):
+        self._ck(self.lib.pgb200_xchg_setup(self.h, cap_tuples))
+
+    def xchg_export(self, buf) -> bytes:
+        h = C.create_string_buffer(64)
+        self._ck(self.lib.pgb200_xchg_export(self.h, buf, h))
+        return h.raw
+
+    def xchg_import(self, peer, buf, handle: bytes):
+        h = C.create_string_buffer(handle, 64)
+        self._ck(self.lib.pgb200_xchg_import(self.h, peer, buf, h))
+
+    def xchg_counts(self):
+        w = max(1, self.params.world)
+        c = (C.c_uint64 * w)()
+        self._ck(self.lib.pgb200_xchg_counts(self.h, c))
+        return list(c)
+
+    def xchg_scatter(self, buf, base):
+        b = (C.c_uint64 * len(base))(*base)
+        self._ck(self.lib.pgb200_xchg_scatter(self.h, buf, b))
+
+    def xchg_apply(self, buf, n):
+        self._ck(self.lib.pgb200_xchg_apply(self.h, buf, n))
 
     def finish_pass1(self) -> Pass1Stats:
         st = Pass1Stats()

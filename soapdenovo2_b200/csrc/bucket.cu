@@ -12,6 +12,7 @@
 #include "engine_impl.cuh"
 #include "scan.cuh"
 #include "chop.cuh"
+#include <cstring>
 
 namespace pgb {
 
@@ -76,6 +77,13 @@ struct TileOffOut {
     __device__ void operator()(u64 i, u64 prefix, u64) const { u64 b = i / n_tiles, t = i - b * n_tiles; off[t * NB + b] = (u32)prefix; }
 };
 
+// Fused exchange: owner o's tuples are stored STRAIGHT into rank o's receive buffer (a peer-mapped pointer, NVLink stores)
+// instead of into a local send buffer that NCCL would copy later: dst[o].ptr already points at this rank's slice.
+struct PeerDst {
+    u64* ptr;     // where this rank's first tuple for owner o goes (peer or local memory)
+    u64 start;    // local tuple index of owner o's range (offsets from the counting sort are relative to it)
+};
+
 template <int NW>
 struct ScatterSink {
     unsigned* cursor;
@@ -83,10 +91,13 @@ struct ScatterSink {
     u64 ord;
     u64 mask;
     int region_shift, region_bits, world;
+    const PeerDst* peers;   // nullptr: plain local buffer
     __device__ __forceinline__ void operator()(const Kmer<NW>& canon, unsigned left, unsigned right, int j) {
         unsigned b = bucket_of(canon, mask, region_shift, region_bits, world);
         u64 p = atomicAdd(&cursor[b], 1u);
-        u64* t = tuples + p * TupleW<NW>::value;
+        u64* t;
+        if (peers) { PeerDst d = peers[b >> region_bits]; t = d.ptr + (p - d.start) * TupleW<NW>::value; }
+        else t = tuples + p * TupleW<NW>::value;
         u64 m = tuple_meta(ord, j, left, right);
         if (NW == 2) {
             asm volatile("st.global.cs.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(t), "l"(canon.w[0]), "l"(canon.w[1]), "l"(m), "l"(0ull) : "memory");
@@ -100,7 +111,8 @@ struct ScatterSink {
 template <int NW>
 __global__ void __launch_bounds__(BK_THREADS) k_bucket_scatter(KParams<NW> kp, const u64* __restrict__ words, const u32* __restrict__ lens, u64 n_rec,
                                                                 int W64, u64 ord_base, u64 ord_stride, u64 mask, int region_shift, int region_bits,
-                                                                int world, int NB, const u32* tileoff, u64* tuples, int rpt, u64 tile0) {
+                                                                int world, int NB, const u32* tileoff, u64* tuples, int rpt, u64 tile0,
+                                                                const PeerDst* peers) {
     extern __shared__ unsigned s_cur[];
     const u32* row = tileoff + (tile0 + blockIdx.x) * NB;
     for (int b = threadIdx.x; b < NB; b += BK_THREADS) s_cur[b] = row[b];
@@ -110,7 +122,7 @@ __global__ void __launch_bounds__(BK_THREADS) k_bucket_scatter(KParams<NW> kp, c
         if (r < n_rec) {
             int L = (int)lens[r];
             if (L >= kp.K + 1) {
-                ScatterSink<NW> sink{s_cur, tuples, ord_base + r * ord_stride, mask, region_shift, region_bits, world};
+                ScatterSink<NW> sink{s_cur, tuples, ord_base + r * ord_stride, mask, region_shift, region_bits, world, peers};
                 chop_read(kp, words + r * (u64)W64, L, sink);
             }
         }
@@ -151,11 +163,11 @@ __global__ void __launch_bounds__(BK_THREADS) k_apply_tuples(Table<NW> tab, cons
 }
 
 template <int NW>
-void EngineT<NW>::bucket_chunk(const ReadChunk& ch) { bucket_chunks(&ch, 1, prm_.world > 1 ? 0 : (8ull << 20), 1); }
+void EngineT<NW>::bucket_chunk(const ReadChunk& ch) { bucket_chunks(&ch, 1, prm_.world > 1 ? 0 : (8ull << 20), 1, !xchg_fused_); }
 
 // Counting sort of the tuples of `n` chunks by (owner, table region of ~region_bytes).  rpt = reads per thread (tile size).
 template <int NW>
-void EngineT<NW>::bucket_chunks(const ReadChunk* chs, size_t n, u64 region_bytes, int rpt) {
+void EngineT<NW>::bucket_chunks(const ReadChunk* chs, size_t n, u64 region_bytes, int rpt, bool scatter_now) {
     const int world = prm_.world > 1 ? prm_.world : 1;
     int log2cap = 0;
     while ((1ull << log2cap) < cap_) log2cap++;
@@ -202,16 +214,79 @@ void EngineT<NW>::bucket_chunks(const ReadChunk* chs, size_t n, u64 region_bytes
     if (n_tuples_ >= 0xFFFFFFFFull) throw std::runtime_error("pgb200: more than 2^32 k-mer instances in one batch; use a smaller batch");
     owner_start_.assign(world + 1, n_tuples_);
     for (int o = 0; o < world; o++) owner_start_[o] = first_row[(size_t)o << rb];
+    bk_ = BucketGeom{region_shift, rb, NB, rpt, tile0};
+    if (!scatter_now) return;
     tuple_flip_ ^= 1;
     tuple_buf().ensure((n_tuples_ + 1) * TupleW<NW>::value * sizeof(u64));
+    bucket_scatter(chs, n, tuple_buf().template as<u64>(), nullptr);
+}
+
+template <int NW>
+void EngineT<NW>::bucket_scatter(const ReadChunk* chs, size_t n, u64* tuples, const void* peers) {
+    const int world = prm_.world > 1 ? prm_.world : 1;
+    size_t smem = (size_t)bk_.NB * sizeof(unsigned);
     for (size_t c = 0; c < n; c++) {
         if (!chs[c].n_rec) continue;
-        k_bucket_scatter<NW><<<(unsigned)(tile0[c + 1] - tile0[c]), BK_THREADS, smem, st_>>>(kp_, chs[c].words, chs[c].len, chs[c].n_rec, W64_, chs[c].ord_base,
-                                                                                            chs[c].ord_stride, tab_.mask, region_shift, rb, world, NB,
-                                                                                            tileoff_buf_.template as<u32>(), tuple_buf().template as<u64>(), rpt, tile0[c]);
+        k_bucket_scatter<NW><<<(unsigned)(bk_.tile0[c + 1] - bk_.tile0[c]), BK_THREADS, smem, st_>>>(
+            kp_, chs[c].words, chs[c].len, chs[c].n_rec, W64_, chs[c].ord_base, chs[c].ord_stride, tab_.mask, bk_.region_shift, bk_.rb, world, bk_.NB,
+            tileoff_buf_.template as<u32>(), tuples, bk_.rpt, bk_.tile0[c], reinterpret_cast<const PeerDst*>(peers));
     }
     PG_CUDA(cudaGetLastError());
     p1_.launches += 3 + 2 * n;
+}
+
+// ---------------------------------------------------------------- fused exchange (peer stores over NVLink)
+template <int NW>
+void EngineT<NW>::xchg_setup(uint64_t cap_tuples) {
+    xchg_cap_ = cap_tuples;
+    for (int b = 0; b < 2; b++) xchg_recv_[b].alloc((cap_tuples + 1) * TupleW<NW>::value * sizeof(u64));
+    xchg_peer_[0].assign(prm_.world, nullptr);
+    xchg_peer_[1].assign(prm_.world, nullptr);
+    for (int b = 0; b < 2; b++) xchg_peer_[b][prm_.rank] = xchg_recv_[b].p;
+    xchg_dst_.alloc(prm_.world * sizeof(PeerDst));
+    xchg_fused_ = true;
+}
+template <int NW>
+void EngineT<NW>::xchg_export(int buf, void* handle64) {
+    cudaIpcMemHandle_t h;
+    PG_CUDA(cudaIpcGetMemHandle(&h, xchg_recv_[buf].p));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+}
+template <int NW>
+void EngineT<NW>::xchg_import(int peer, int buf, const void* handle64) {
+    if (peer == prm_.rank) return;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    PG_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    xchg_peer_[buf][peer] = p;
+}
+template <int NW>
+void EngineT<NW>::xchg_counts(uint64_t* counts) {
+    const int world = prm_.world;
+    for (int o = 0; o < world; o++) counts[o] = owner_start_.size() == (size_t)world + 1 ? owner_start_[o + 1] - owner_start_[o] : 0;
+}
+// base[o] = tuple index inside rank o's receive buffer where this rank's slice starts
+template <int NW>
+void EngineT<NW>::xchg_scatter(int buf, const uint64_t* base) {
+    const int world = prm_.world;
+    if (owner_start_.size() != (size_t)world + 1 || !n_tuples_) { sync(); return; }
+    std::vector<PeerDst> d(world);
+    for (int o = 0; o < world; o++) {
+        u64 cnt = owner_start_[o + 1] - owner_start_[o];
+        if (base[o] + cnt > xchg_cap_) throw std::runtime_error("pgb200: fused exchange receive buffer too small");
+        if (!xchg_peer_[buf][o]) throw std::runtime_error("pgb200: fused exchange peer buffer not imported");
+        d[o].ptr = reinterpret_cast<u64*>(xchg_peer_[buf][o]) + base[o] * TupleW<NW>::value;
+        d[o].start = owner_start_[o];
+    }
+    PG_CUDA(cudaMemcpyAsync(xchg_dst_.p, d.data(), world * sizeof(PeerDst), cudaMemcpyHostToDevice, st_));
+    bucket_scatter(&chunks_.back(), 1, nullptr, xchg_dst_.p);
+    sync();   // all peer stores of this rank are performed; the caller's barrier makes every rank's visible
+}
+template <int NW>
+void EngineT<NW>::xchg_apply(int buf, uint64_t n) {
+    apply_received(xchg_recv_[buf].p, n);
 }
 
 // Batch mode (single GPU): every chunk fed since the last flush is bucketed by 32 MB table region in ONE counting sort and applied
@@ -226,7 +301,7 @@ void EngineT<NW>::flush_batch() {
     PG_CUDA(cudaEventRecord(ev_[0], st_));
     PG_CUDA(cudaEventRecord(ev_[1], st_));
     PG_CUDA(cudaEventRecord(ev_[2], st_));
-    bucket_chunks(chunks_.data() + pending_first_, chunks_.size() - pending_first_, 32ull << 20, 4);
+    bucket_chunks(chunks_.data() + pending_first_, chunks_.size() - pending_first_, 32ull << 20, 4, true);
     apply_tuples(tuple_buf().template as<u64>(), n_tuples_);
     PG_CUDA(cudaEventRecord(ev_[3], st_));
     timing_pending_ = true;
@@ -245,8 +320,16 @@ void EngineT<NW>::apply_tuples(const u64* tuples, u64 n) {
 }
 
 template void EngineT<2>::bucket_chunk(const ReadChunk&);
-template void EngineT<2>::bucket_chunks(const ReadChunk*, size_t, u64, int);
-template void EngineT<4>::bucket_chunks(const ReadChunk*, size_t, u64, int);
+template void EngineT<2>::bucket_chunks(const ReadChunk*, size_t, u64, int, bool);
+template void EngineT<4>::bucket_chunks(const ReadChunk*, size_t, u64, int, bool);
+template void EngineT<2>::bucket_scatter(const ReadChunk*, size_t, u64*, const void*);
+template void EngineT<4>::bucket_scatter(const ReadChunk*, size_t, u64*, const void*);
+template void EngineT<2>::xchg_setup(uint64_t); template void EngineT<4>::xchg_setup(uint64_t);
+template void EngineT<2>::xchg_export(int, void*); template void EngineT<4>::xchg_export(int, void*);
+template void EngineT<2>::xchg_import(int, int, const void*); template void EngineT<4>::xchg_import(int, int, const void*);
+template void EngineT<2>::xchg_counts(uint64_t*); template void EngineT<4>::xchg_counts(uint64_t*);
+template void EngineT<2>::xchg_scatter(int, const uint64_t*); template void EngineT<4>::xchg_scatter(int, const uint64_t*);
+template void EngineT<2>::xchg_apply(int, uint64_t); template void EngineT<4>::xchg_apply(int, uint64_t);
 template void EngineT<2>::flush_batch();
 template void EngineT<4>::flush_batch();
 template void EngineT<4>::bucket_chunk(const ReadChunk&);

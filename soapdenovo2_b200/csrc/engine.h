@@ -72,6 +72,13 @@ public:
     virtual const void* exchange_buffer(uint64_t* ranges /*world+1*/, int* tuple_bytes) = 0;
     virtual void exchange_clear() = 0;
     virtual void apply_received(const void* dev_tuples, uint64_t n) = 0;
+    // fused exchange (peer stores over NVLink instead of a library all-to-all): see include/pregraph_b200.h, pgb200_xchg_*
+    virtual void xchg_setup(uint64_t cap_tuples) = 0;
+    virtual void xchg_export(int buf, void* handle64) = 0;
+    virtual void xchg_import(int peer, int buf, const void* handle64) = 0;
+    virtual void xchg_counts(uint64_t* counts) = 0;
+    virtual void xchg_scatter(int buf, const uint64_t* base) = 0;
+    virtual void xchg_apply(int buf, uint64_t n) = 0;
     virtual void finish_pass1(Pass1Stats* st) = 0;
     virtual void reset_pass1() = 0;   // drop reads + table (bench: repeat the step)
     virtual void sweeps(SweepStats* st) = 0;            // delow + mark linear + kmerFreq histogram

@@ -121,7 +121,14 @@ public:
     int n_buckets_ = 0, region_bits_ = 0;
     std::vector<u64> owner_start_;   // [world + 1] tuple offsets of each owner's range in tuple_buf_
     void bucket_chunk(const ReadChunk& ch);
-    void bucket_chunks(const ReadChunk* chs, size_t n, u64 region_bytes, int rpt);
+    void bucket_chunks(const ReadChunk* chs, size_t n, u64 region_bytes, int rpt, bool scatter_now);
+    void bucket_scatter(const ReadChunk* chs, size_t n, u64* tuples, const void* peers);
+    struct BucketGeom { int region_shift = 0, rb = 0, NB = 0, rpt = 1; std::vector<u64> tile0; } bk_;
+    // fused exchange: receive buffers other ranks store into directly (CUDA IPC peer mappings over NVLink)
+    bool xchg_fused_ = false;
+    u64 xchg_cap_ = 0;
+    DevBuf xchg_recv_[2], xchg_dst_;
+    std::vector<void*> xchg_peer_[2];
     // batch mode (PGB200_BATCH_GB > 0): inserts are deferred and done region-sorted over many chunks at once
     double batch_gb_ = 0;
     size_t pending_first_ = 0;   // chunks_[pending_first_..) are decoded but not inserted yet
@@ -131,6 +138,12 @@ public:
 public:
     // multi-GPU exchange surface (C-ABI: pgb200_exchange_*)
     static constexpr int tuple_words() { return NW == 2 ? 4 : 8; }
+    void xchg_setup(uint64_t cap_tuples) override;
+    void xchg_export(int buf, void* handle64) override;
+    void xchg_import(int peer, int buf, const void* handle64) override;
+    void xchg_counts(uint64_t* counts) override;
+    void xchg_scatter(int buf, const uint64_t* base) override;
+    void xchg_apply(int buf, uint64_t n) override;
     const void* exchange_buffer(uint64_t* ranges, int* tuple_bytes) override {
         const int world = prm_.world > 1 ? prm_.world : 1;
         for (int o = 0; o <= world; o++) ranges[o] = owner_start_.size() == (size_t)world + 1 ? owner_start_[o] : 0;

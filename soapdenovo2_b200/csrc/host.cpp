@@ -91,6 +91,12 @@ extern "C" const void* pgb200_exchange_buffer(pgb200_engine* e, uint64_t* ranges
 }
 extern "C" int pgb200_exchange_clear(pgb200_engine* e) { PG_TRY e->e->exchange_clear(); PG_CATCH }
 extern "C" int pgb200_apply_tuples(pgb200_engine* e, const void* dev_tuples, uint64_t n) { PG_TRY e->e->apply_received(dev_tuples, n); PG_CATCH }
+extern "C" int pgb200_xchg_setup(pgb200_engine* e, uint64_t cap_tuples) { PG_TRY e->e->xchg_setup(cap_tuples); PG_CATCH }
+extern "C" int pgb200_xchg_export(pgb200_engine* e, int buf, void* handle64) { PG_TRY e->e->xchg_export(buf, handle64); PG_CATCH }
+extern "C" int pgb200_xchg_import(pgb200_engine* e, int peer, int buf, const void* handle64) { PG_TRY e->e->xchg_import(peer, buf, handle64); PG_CATCH }
+extern "C" int pgb200_xchg_counts(pgb200_engine* e, uint64_t* counts) { PG_TRY e->e->xchg_counts(counts); PG_CATCH }
+extern "C" int pgb200_xchg_scatter(pgb200_engine* e, int buf, const uint64_t* base) { PG_TRY e->e->xchg_scatter(buf, base); PG_CATCH }
+extern "C" int pgb200_xchg_apply(pgb200_engine* e, int buf, uint64_t n) { PG_TRY e->e->xchg_apply(buf, n); PG_CATCH }
 extern "C" int pgb200_finish_pass1(pgb200_engine* e, pgb200_pass1_stats* st) {
     PG_TRY
     Pass1Stats s;

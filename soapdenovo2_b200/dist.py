@@ -91,3 +91,42 @@ class PipelinedExchange:
 
     def finish(self):
         return self._drain()
+
+
+class FusedExchange:
+    """The owner exchange WITHOUT a library collective on the data path: k_bucket_scatter stores every tuple straight into its
+    owner's receive buffer (CUDA IPC peer mapping, NVLink stores) while it chops the next reads.  torch.distributed only carries
+    the 64-byte IPC handles once, an 8-byte-per-pair count matrix per round, and the barrier between "all stores issued" and
+    "apply what arrived".  Two receive buffers alternate, so round i+1 may be scattered while a slow peer still applies round i."""
+
+    def __init__(self, eng, torch, dist, device, cap_tuples):
+        self.eng, self.torch, self.dist, self.device = eng, torch, dist, device
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        eng.xchg_setup(cap_tuples)
+        for buf in (0, 1):
+            mine = torch.tensor(list(eng.xchg_export(buf)), dtype=torch.uint8, device=device)
+            allh = [torch.empty(64, dtype=torch.uint8, device=device) for _ in range(self.world)]
+            dist.all_gather(allh, mine)
+            for p in range(self.world):
+                if p != self.rank:
+                    eng.xchg_import(p, buf, bytes(allh[p].cpu().tolist()))
+        self.buf = 0
+
+    def round(self):
+        torch, dist = self.torch, self.dist
+        mine = torch.tensor(self.eng.xchg_counts(), dtype=torch.int64, device=self.device)
+        rows = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(rows, mine)
+        m = torch.stack(rows).cpu()                       # m[s][o] = tuples rank s holds for owner o
+        base = m[: self.rank].sum(dim=0).tolist() if self.rank else [0] * self.world
+        n_recv = int(m[:, self.rank].sum())
+        self.eng.xchg_scatter(self.buf, [int(b) for b in base])   # returns when this rank's peer stores are performed
+        dist.barrier()                                    # ... and now everybody's are
+        self.eng.xchg_apply(self.buf, n_recv)
+        self.eng.exchange_clear()
+        self.buf ^= 1
+        return n_recv
+
+    def finish(self):
+        self.dist.barrier()
+        return 0

@@ -11,7 +11,7 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, d, out):
+def _worker(rank, world, port, d, out, mode="nccl"):
     import torch.distributed as dist
     from soapdenovo2_b200 import dist as pdist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -30,11 +30,15 @@ def _worker(rank, world, port, d, out):
         for c in range(3):
             part = recs[c * per:(c + 1) * per]
             work.append((b"".join(part), (c * per) * 2 + mate))
+    fused = pdist.FusedExchange(eng, torch, dist, dev, cap_tuples=1 << 20) if mode == "fused" else None
     for r0 in range(0, len(work), world):
         i = r0 + rank
         if i < len(work):
             eng.feed_text(work[i][0], fastq=True, ord_base=work[i][1], ord_stride=2)
-        pdist.exchange_round(eng, torch, dist, dev)
+        if fused:
+            fused.round()
+        else:
+            pdist.exchange_round(eng, torch, dist, dev)
     st = eng.finish_pass1()
     hist, lin, rem = eng.sweeps()
     h = torch.tensor(hist, device=dev, dtype=torch.int64)
@@ -47,7 +51,8 @@ def _worker(rank, world, port, d, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_two_gpu_sharded_pass1(tmp_path):
+@pytest.mark.parametrize("mode", ["nccl", "fused"])
+def test_two_gpu_sharded_pass1(tmp_path, mode):
     import torch.multiprocessing as mp
     util.build_oracle()
     d = str(tmp_path)
@@ -55,7 +60,7 @@ def test_two_gpu_sharded_pass1(tmp_path):
     mod, dump = os.path.join(d, "mod"), os.path.join(d, "mod.table")
     util.run_model(util.MODEL63, cfg, mod, 63, 8, ("-1", "-T", dump, "-a", "1"))
     out = mp.Manager().dict()
-    mp.spawn(_worker, args=(2, 29541, d, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, 29541 if mode == "nccl" else 29543, d, out, mode), nprocs=2, join=True)
     hist, cnt, _ = out[0]
     assert api.kmerfreq_text(hist) == open(mod + ".kmerFreq", "rb").read()
     want = open(dump, "rb").read()
