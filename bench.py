@@ -261,7 +261,7 @@ def main():
 
     xchg = None
     if world > 1:
-        mode = os.environ.get("PGB200_XCHG", "fused")
+        mode = os.environ.get("PGB200_XCHG", "nccl")   # "fused": peer stores over NVLink from the bucketing kernel (dist.FusedExchange)
         xchg = (pdist.FusedExchange(eng, torch, dist, dev, cap_tuples=int(2.2 * args.chunk_reads * (RD_LEN - K + 1)))
                 if mode == "fused" else pdist.PipelinedExchange(eng, torch, dist, dev))
 

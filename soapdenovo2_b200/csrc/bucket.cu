@@ -37,7 +37,11 @@ struct CountSink {
     u64 mask;
     int region_shift, region_bits, world;
     __device__ __forceinline__ void operator()(const Kmer<NW>& canon, unsigned, unsigned, int) {
-        atomicAdd(&hist[bucket_of(canon, mask, region_shift, region_bits, world)], 1u);
+        unsigned b = bucket_of(canon, mask, region_shift, region_bits, world);
+        if (region_bits == 0) {   // few buckets (owners only): one shared-memory atomic per warp and owner instead of one per lane
+            unsigned m = __match_any_sync(__activemask(), b);
+            if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&hist[b], (unsigned)__popc(m));
+        } else atomicAdd(&hist[b], 1u);
     }
 };
 
@@ -94,7 +98,17 @@ struct ScatterSink {
     const PeerDst* peers;   // nullptr: plain local buffer
     __device__ __forceinline__ void operator()(const Kmer<NW>& canon, unsigned left, unsigned right, int j) {
         unsigned b = bucket_of(canon, mask, region_shift, region_bits, world);
-        u64 p = atomicAdd(&cursor[b], 1u);
+        u64 p;
+        if (region_bits == 0) {
+            // warp-aggregated cursor: the lanes that go to the same owner take CONSECUTIVE tuple slots, so their 32-byte stores
+            // coalesce into a few long transactions -- what makes direct peer stores over NVLink efficient
+            unsigned m = __match_any_sync(__activemask(), b);
+            int leader = __ffs(m) - 1, lane = threadIdx.x & 31;
+            unsigned base = 0;
+            if (lane == leader) base = atomicAdd(&cursor[b], (unsigned)__popc(m));
+            base = __shfl_sync(m, base, leader);
+            p = base + __popc(m & ((1u << lane) - 1));
+        } else p = atomicAdd(&cursor[b], 1u);
         u64* t;
         if (peers) { PeerDst d = peers[b >> region_bits]; t = d.ptr + (p - d.start) * TupleW<NW>::value; }
         else t = tuples + p * TupleW<NW>::value;
@@ -163,7 +177,7 @@ __global__ void __launch_bounds__(BK_THREADS) k_apply_tuples(Table<NW> tab, cons
 }
 
 template <int NW>
-void EngineT<NW>::bucket_chunk(const ReadChunk& ch) { bucket_chunks(&ch, 1, prm_.world > 1 ? 0 : (8ull << 20), 1, !xchg_fused_); }
+void EngineT<NW>::bucket_chunk(const ReadChunk& ch) { bucket_chunks(&ch, 1, prm_.world > 1 ? (xchg_fused_ ? 1 : 0) : (8ull << 20), 1, !xchg_fused_); }
 
 // Counting sort of the tuples of `n` chunks by (owner, table region of ~region_bytes).  rpt = reads per thread (tile size).
 template <int NW>
@@ -175,6 +189,7 @@ void EngineT<NW>::bucket_chunks(const ReadChunk* chs, size_t n, u64 region_bytes
     int rb = 0;
     int region_shift;
     if (region_bytes == 0) { rb = 6; region_shift = -1; }   // pseudo regions (see bucket_of)
+    else if (region_bytes == 1) { rb = 0; region_shift = 0; }   // owners only (fused peer-store exchange: warp-aggregated cursors)
     else {
         while ((table_bytes >> rb) > region_bytes && rb < 12 && world * (2 << rb) <= 8192) rb++;
         if (rb > log2cap) rb = log2cap;
@@ -284,9 +299,32 @@ void EngineT<NW>::xchg_scatter(int buf, const uint64_t* base) {
     bucket_scatter(&chunks_.back(), 1, nullptr, xchg_dst_.p);
     sync();   // all peer stores of this rank are performed; the caller's barrier makes every rank's visible
 }
+// Apply what the peers stored into receive buffer `buf`, on a SECOND stream and without waiting for it: the random-access apply of
+// round i overlaps the decode / count / peer-store scatter of round i+1 (different bottlenecks: HBM row accesses vs ALU + NVLink).
 template <int NW>
 void EngineT<NW>::xchg_apply(int buf, uint64_t n) {
-    apply_received(xchg_recv_[buf].p, n);
+    sync_apply();                                   // round i-1's apply (normally long finished); settles its timing
+    if (!n) return;
+    create_table_if_needed();
+    PG_CUDA(cudaMemcpyAsync(h_cnt_, d_cnt_, C_COUNT * sizeof(u64), cudaMemcpyDeviceToHost, st_apply_));
+    PG_CUDA(cudaStreamSynchronize(st_apply_));
+    ensure_table_bound(h_cnt_[C_DISTINCT], n);      // growth (rare) happens here, with nothing else touching the table
+    PG_CUDA(cudaEventRecord(ev_apply_[0], st_apply_));
+    unsigned blocks = (unsigned)((n + BK_THREADS - 1) / BK_THREADS);
+    k_apply_tuples<NW><<<blocks, BK_THREADS, 0, st_apply_>>>(tab_, reinterpret_cast<const u64*>(xchg_recv_[buf].p), n, d_cnt_);
+    PG_CUDA(cudaGetLastError());
+    PG_CUDA(cudaEventRecord(ev_apply_[1], st_apply_));
+    apply_inflight_ = true;
+    p1_.launches += 1;
+}
+template <int NW>
+void EngineT<NW>::sync_apply() {
+    if (!apply_inflight_) return;
+    PG_CUDA(cudaEventSynchronize(ev_apply_[1]));
+    float ms;
+    PG_CUDA(cudaEventElapsedTime(&ms, ev_apply_[0], ev_apply_[1]));
+    p1_.ms_insert += ms;
+    apply_inflight_ = false;
 }
 
 // Batch mode (single GPU): every chunk fed since the last flush is bucketed by 32 MB table region in ONE counting sort and applied
@@ -330,6 +368,7 @@ template void EngineT<2>::xchg_import(int, int, const void*); template void Engi
 template void EngineT<2>::xchg_counts(uint64_t*); template void EngineT<4>::xchg_counts(uint64_t*);
 template void EngineT<2>::xchg_scatter(int, const uint64_t*); template void EngineT<4>::xchg_scatter(int, const uint64_t*);
 template void EngineT<2>::xchg_apply(int, uint64_t); template void EngineT<4>::xchg_apply(int, uint64_t);
+template void EngineT<2>::sync_apply(); template void EngineT<4>::sync_apply();
 template void EngineT<2>::flush_batch();
 template void EngineT<4>::flush_batch();
 template void EngineT<4>::bucket_chunk(const ReadChunk&);

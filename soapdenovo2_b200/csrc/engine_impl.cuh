@@ -129,6 +129,10 @@ public:
     u64 xchg_cap_ = 0;
     DevBuf xchg_recv_[2], xchg_dst_;
     std::vector<void*> xchg_peer_[2];
+    cudaStream_t st_apply_ = nullptr;
+    cudaEvent_t ev_apply_[2] = {nullptr, nullptr};
+    bool apply_inflight_ = false;
+    void sync_apply();
     // batch mode (PGB200_BATCH_GB > 0): inserts are deferred and done region-sorted over many chunks at once
     double batch_gb_ = 0;
     size_t pending_first_ = 0;   // chunks_[pending_first_..) are decoded but not inserted yet

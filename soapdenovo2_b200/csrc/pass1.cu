@@ -490,7 +490,8 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     }
     PG_CUDA(cudaEventRecord(ev_[1], st_));
     // table capacity for the worst case of this chunk (host-side bound: no sync; growth itself syncs when it happens)
-    {
+    if (xchg_fused_) create_table_if_needed();   // an apply may be in flight on the other stream: growth is decided in xchg_apply
+    else {
         int per_read = maxlen - prm_.K + 1;
         ensure_table_bound(have_distinct, per_read > 0 ? n_rec * (u64)per_read : 0);
     }
@@ -547,6 +548,7 @@ void EngineT<NW>::settle_timing() {
 
 template <int NW>
 void EngineT<NW>::finish_pass1(Pass1Stats* st) {
+    sync_apply();
     flush_batch();
     settle_timing();
     read_counters();
@@ -562,6 +564,7 @@ void EngineT<NW>::finish_pass1(Pass1Stats* st) {
 template <int NW>
 void EngineT<NW>::reset_pass1() {
     double t0 = host_now();
+    sync_apply();
     settle_timing();
     sync();
     chunks_.clear();
@@ -620,6 +623,7 @@ __global__ void __launch_bounds__(256) k_sweep(Table<NW> tab, int D, u64* hist, 
 template <int NW>
 void EngineT<NW>::sweeps(SweepStats* st) {
     double t0 = host_now();
+    sync_apply();
     flush_batch();
     DevBuf hist;
     hist.alloc(256 * sizeof(u64));
@@ -652,6 +656,8 @@ EngineT<NW>::EngineT(const PgParams& p) : prm_(p) {
     kp_ = make_kparams<NW>(p.K);
     PG_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     PG_CUDA(cudaStreamCreateWithFlags(&st_copy_, cudaStreamNonBlocking));
+    PG_CUDA(cudaStreamCreateWithFlags(&st_apply_, cudaStreamNonBlocking));
+    for (auto& e : ev_apply_) PG_CUDA(cudaEventCreate(&e));
     PG_CUDA(cudaEventCreateWithFlags(&ev_copy_, cudaEventDisableTiming));
     for (auto& e : ev_) PG_CUDA(cudaEventCreate(&e));
     PG_CUDA(cudaMalloc(&d_cnt_, C_COUNT * sizeof(u64)));
@@ -670,6 +676,8 @@ EngineT<NW>::~EngineT() {
     if (d_cnt_) cudaFree(d_cnt_);
     if (h_cnt_) cudaFreeHost(h_cnt_);
     for (auto& e : ev_) if (e) cudaEventDestroy(e);
+    if (st_apply_) { cudaStreamSynchronize(st_apply_); cudaStreamDestroy(st_apply_); }
+    for (auto& e : ev_apply_) if (e) cudaEventDestroy(e);
     if (ev_copy_) cudaEventDestroy(ev_copy_);
     if (st_copy_) cudaStreamDestroy(st_copy_);
     if (st_) cudaStreamDestroy(st_);
