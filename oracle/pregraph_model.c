@@ -102,7 +102,8 @@ typedef struct {
 } Set;
 
 static int is_prime_kh(u64 n) { /* newhash.c:142-167: float sqrt, strict '<' => squares of primes pass */
-    if (n < 4) return 1; if (n % 2 == 0) return 0;
+    if (n < 4) return 1;
+    if (n % 2 == 0) return 0;
     u64 mx = (u64)sqrt((float)n);
     for (u64 i = 3; i < mx; i += 2) if (n % i == 0) return 0;
     return 1;
@@ -592,7 +593,10 @@ int main(int argc, char **argv) {
         case 'a': initG = atoi(optarg); break; case 'T': tdump = optarg; break; case '1': only1 = 1; break;
     }
     if (!cfg || !prefix) { fprintf(stderr, "usage: pregraph_model -s cfg -o prefix [-K k -p P -a G -d D -R]\n"); return -1; }
-    if (K % 2 == 0) K++; if (K < 13) K = 13; if (K > MODEL_W / 2 - 1) K = MODEL_W / 2 - 1;      /* pregraph.c:71-97 */
+    /* pregraph.c:71-97 */
+    if (K % 2 == 0) K++;
+    if (K < 13) K = 13;
+    if (K > MODEL_W / 2 - 1) K = MODEL_W / 2 - 1;
     D = (signed char)D;                                                   /* deLowKmer is a char (global.h:67) */
     crc_init(); MASKK = kmask(K);
     scan_lib(cfg);
