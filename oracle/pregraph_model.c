@@ -238,7 +238,8 @@ static Src src_open(const char *fn, int fastq) {
     fprintf(stderr, "Import reads from file:\n %s\n", fn);
     FILE *f = fopen(fn, "rb"); if (!f) { fprintf(stderr, "Cannot open %s. Now exit to system...\n", fn); exit(-1); }
     Src s; fseek(f, 0, SEEK_END); s.n = ftell(f); fseek(f, 0, SEEK_SET); s.buf = malloc(s.n + 1);
-    if (fread(s.buf, 1, s.n, f) != s.n) exit(-1); s.buf[s.n] = 0; fclose(f); s.pos = 0; s.fastq = fastq; return s;
+    if (fread(s.buf, 1, s.n, f) != s.n) exit(-1);
+    s.buf[s.n] = 0; fclose(f); s.pos = 0; s.fastq = fastq; return s;
 }
 static size_t line_end(const Src *s, size_t p) { while (p < s->n && s->buf[p] != '\n') p++; return p; }
 /* one record -> base codes.  readseqInBuf readseq1by1.c:138-209 / readseqfq :279-360: first min(linelen, maxReadLen) chars of the
