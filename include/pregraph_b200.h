@@ -111,6 +111,10 @@ int pgb200_kmer2edges(pgb200_engine *e, const char *outfile_prefix, pgb200_graph
 int pgb200_read2edge(pgb200_engine *e, const char *outfile_prefix, pgb200_graph_stats *st);
 int pgb200_output_vertex(pgb200_engine *e, const char *outfile_prefix, pgb200_graph_stats *st);
 
+/* Host logic only (no GPU): the read-stream plan of a library config -- one "mate fastq reverse_seq cut path" line per file in
+ * the order the reference opens them (scan_libInfo lib.c:130-506, nextValidIndex readseq1by1.c:595-674); first line "max_rd_len N". */
+int pgb200_plan_files(const char *cfg, char *out, size_t cap);
+
 /* The drop-in stage entry points. */
 int pgb200_pregraph_main(int argc, char **argv, int flavour127);
 int call_pregraph(int argc, char **argv);

@@ -18,7 +18,7 @@ EXPORTS = [
     "pgb200_feed_text", "pgb200_last_chunk_records", "pgb200_exchange_buffer", "pgb200_exchange_clear", "pgb200_apply_tuples",
     "pgb200_xchg_setup", "pgb200_xchg_export", "pgb200_xchg_import", "pgb200_xchg_counts", "pgb200_xchg_scatter", "pgb200_xchg_apply", "pgb200_finish_pass1", "pgb200_reset_pass1", "pgb200_sweeps",
     "pgb200_build_layout", "pgb200_node_count", "pgb200_dump_nodes", "pgb200_remove_tips", "pgb200_kmer2edges",
-    "pgb200_read2edge", "pgb200_output_vertex", "pgb200_pregraph_main", "call_pregraph",
+    "pgb200_read2edge", "pgb200_output_vertex", "pgb200_plan_files", "pgb200_pregraph_main", "call_pregraph",
 ]
 
 
@@ -79,6 +79,7 @@ def load():
         getattr(lib, fn).argtypes = [C.c_void_p, C.POINTER(GraphStats)]
     for fn in ("pgb200_kmer2edges", "pgb200_read2edge", "pgb200_output_vertex"):
         getattr(lib, fn).argtypes = [C.c_void_p, C.c_char_p, C.POINTER(GraphStats)]
+    lib.pgb200_plan_files.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
     lib.pgb200_pregraph_main.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int]
     _lib = lib
     return lib
@@ -202,6 +203,20 @@ class PregraphEngine:
 
     def output_vertex(self, prefix):
         self._ck(self.lib.pgb200_output_vertex(self.h, prefix.encode(), C.byref(self.graph)))
+
+
+def plan_files(cfg: str):
+    """Host logic only: [(mate, fastq, reverse_seq, cut, path)] in the order the reference opens the files, and max_rd_len."""
+    lib = load()
+    buf = C.create_string_buffer(1 << 20)
+    if lib.pgb200_plan_files(cfg.encode(), buf, len(buf)):
+        raise EngineError("plan too large")
+    lines = buf.value.decode().splitlines()
+    plan = []
+    for l in lines[1:]:
+        m, fq, rev, cut, path = l.split(" ", 4)
+        plan.append((int(m), int(fq), int(rev), int(cut), path))
+    return int(lines[0].split()[1]), plan
 
 
 def kmerfreq_text(hist) -> bytes:

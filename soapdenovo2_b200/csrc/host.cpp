@@ -253,6 +253,48 @@ static void scan_lib(const char* cfg, std::vector<Lib>& libs, int& max_rd_len) {
     std::stable_sort(libs.begin(), libs.end(), [](const Lib& x, const Lib& y) { return x.avg_ins < y.avg_ins; });   // qsort by avg_ins, lib.c:505
 }
 
+// ------------------------------------------------------------------------------------------------ the read-stream plan
+// One entry per file in the order the reference opens them (openNextFile / nextValidIndex): libraries sorted by avg_ins, only
+// asm_flags 1|3; inside a library f1/f2 pairs, q1/q2 pairs, p, (b: unsupported), f, q.  Mates share an ordinal range with stride 2.
+struct PlanEntry {
+    std::string path;
+    bool fastq;
+    int mate;        // -1 single file; 0/1 = first/second file of an interleaved pair
+    int reverse, cut;
+};
+static std::vector<PlanEntry> build_plan(const std::vector<Lib>& libs, int max_rd_len) {
+    std::vector<PlanEntry> plan;
+    for (const Lib& L : libs) {
+        if (L.asm_flag != 1 && L.asm_flag != 3) continue;                           // nextValidIndex, readseq1by1.c:601
+        int cut = (L.rd_len_cutoff > 0 && L.rd_len_cutoff < max_rd_len) ? L.rd_len_cutoff : max_rd_len;   // prlHashReads.c:921-928
+        for (int type = 1; type <= 6; type++) {
+            if (type == 4) continue;
+            bool fq = (type == 2 || type == 6);
+            for (size_t fi = 0; fi < L.f[type].size(); fi++) {
+                if (type <= 2) {
+                    plan.push_back({L.f[type][fi], fq, 0, L.reverse, cut});
+                    plan.push_back({L.f[type == 1 ? 0 : 4][fi], fq, 1, L.reverse, cut});
+                } else plan.push_back({L.f[type][fi], fq, -1, L.reverse, cut});
+            }
+        }
+    }
+    return plan;
+}
+
+// CPU-testable view of the host logic: "mate fastq reverse cut path" per line, in stream order
+extern "C" int pgb200_plan_files(const char* cfg, char* out, size_t cap) {
+    std::vector<Lib> libs;
+    int max_rd_len = 0;
+    scan_lib(cfg, libs, max_rd_len);
+    if (!max_rd_len) max_rd_len = 100;
+    std::string s = "max_rd_len " + std::to_string(max_rd_len) + "\n";
+    for (const PlanEntry& e : build_plan(libs, max_rd_len))
+        s += std::to_string(e.mate) + " " + std::to_string((int)e.fastq) + " " + std::to_string(e.reverse) + " " + std::to_string(e.cut) + " " + e.path + "\n";
+    if (s.size() + 1 > cap) return -1;
+    memcpy(out, s.c_str(), s.size() + 1);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ streaming a file into the engine
 // Chunks are cut at record boundaries on the host (only the tail of each chunk is inspected); the GPU does the parsing.
 static size_t last_record_start(const char* buf, size_t n, bool fastq) {
@@ -390,24 +432,19 @@ extern "C" int pgb200_pregraph_main(int argc, char** argv, int flavour127) {
     {
         Feeder fd;
         fd.eng = eng;
-        for (const Lib& L : libs) {
-            if (L.asm_flag != 1 && L.asm_flag != 3) continue;                           // nextValidIndex, readseq1by1.c:601
-            int cut = (L.rd_len_cutoff > 0 && L.rd_len_cutoff < max_rd_len) ? L.rd_len_cutoff : max_rd_len;   // prlHashReads.c:921-928
-            for (int type = 1; type <= 6; type++) {
-                if (type == 4) continue;
-                bool fq = (type == 2 || type == 6);
-                for (size_t fi = 0; fi < L.f[type].size(); fi++) {
-                    if (type <= 2) {
-                        // mates interleave r1,r2,r1,r2 (prlHashReads.c:480-583): ordinal = base + 2*pair + mate
-                        uint64_t n1 = fd.run(L.f[type][fi], fq, ord_next, 2, L.reverse, cut);
-                        uint64_t n2 = fd.run(L.f[type == 1 ? 0 : 4][fi], fq, ord_next + 1, 2, L.reverse, cut);
-                        if (n1 != n2) { fprintf(stderr, "pgb200: mate files hold different numbers of reads (%llu vs %llu): unsupported\n", (unsigned long long)n1, (unsigned long long)n2); exit(-1); }
-                        ord_next += 2 * n1; n_reads += 2 * n1;
-                    } else {
-                        uint64_t n = fd.run(L.f[type][fi], fq, ord_next, 1, L.reverse, cut);
-                        ord_next += n; n_reads += n;
-                    }
-                }
+        std::vector<PlanEntry> plan = build_plan(libs, max_rd_len);
+        for (size_t i = 0; i < plan.size(); i++) {
+            const PlanEntry& e = plan[i];
+            if (e.mate == 0) {
+                // mates interleave r1,r2,r1,r2 (prlHashReads.c:480-583): ordinal = base + 2*pair + mate
+                uint64_t n1 = fd.run(e.path, e.fastq, ord_next, 2, e.reverse, e.cut);
+                const PlanEntry& m = plan[++i];
+                uint64_t n2 = fd.run(m.path, m.fastq, ord_next + 1, 2, m.reverse, m.cut);
+                if (n1 != n2) { fprintf(stderr, "pgb200: mate files hold different numbers of reads (%llu vs %llu): unsupported\n", (unsigned long long)n1, (unsigned long long)n2); exit(-1); }
+                ord_next += 2 * n1; n_reads += 2 * n1;
+            } else {
+                uint64_t n = fd.run(e.path, e.fastq, ord_next, 1, e.reverse, e.cut);
+                ord_next += n; n_reads += n;
             }
         }
     }
