@@ -444,7 +444,7 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     scan_buf_.ensure(scan_scratch_elems(groups) * sizeof(u64));
     NlIn in{reinterpret_cast<const uint4*>(d_text), (u64)nbytes};
     // pass A: count lines
-    device_scan(in, NlCountOut{}, groups, scan_buf_.template as<u64>(), d_cnt_ + C_MISC0, st_);
+    device_scan_total(in, groups, scan_buf_.template as<u64>(), d_cnt_ + C_MISC0, st_);   // tile bases stay in scan_buf_
     // ONE host sync per chunk: line count, last byte, and the counters as of the previous chunk's insert
     unsigned char* h_last = reinterpret_cast<unsigned char*>(h_cnt_ + C_COUNT);
     PG_CUDA(cudaMemcpyAsync(h_last, d_text + nbytes - 1, 1, cudaMemcpyDeviceToHost, st_));
@@ -466,7 +466,7 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
         // only FASTQ can end without newline inside the quality line; the sequence line end is always a real '\n'
         PG_CUDA(cudaMemsetAsync(seq_end, 0, n_rec * sizeof(u64), st_));
     }
-    device_scan(in, NlOut{in, seq_start, seq_end, n_rec, lpr}, groups, scan_buf_.template as<u64>(), d_cnt_ + C_MISC0, st_);
+    device_scan_finish(in, NlOut{in, seq_start, seq_end, n_rec, lpr}, groups, scan_buf_.template as<u64>(), st_);
     if (open_tail && !fastq) {
         u64 e = nbytes;
         PG_CUDA(cudaMemcpyAsync(seq_end + n_rec - 1, &e, sizeof e, cudaMemcpyHostToDevice, st_));
@@ -527,7 +527,7 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     if (host_src) PG_CUDA(cudaEventSynchronize(ev_copy_));   // the caller may reuse its host buffer; the insert keeps running
     else if (prm_.world > 1) sync();                          // exchange buffer is read by the caller next
     if (l2gran_mode_ == 2) { sync(); cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 128); }
-    p1_.launches += 8;
+    p1_.launches += 5;   // tile sums, small scan, index apply, decode, insert
     last_records_ = n_rec;
     total_records_ += n_rec;
     t_e = host_now();

@@ -128,4 +128,21 @@ void device_scan(In in, Out out, u64 n, u64* scratch, u64* d_total, cudaStream_t
     k_scan_apply<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, out, n, sums);
 }
 
+// Split form for the case "total first, then (after the caller has sized its outputs) the prefixes": phase 1 leaves the scanned
+// tile bases in `scratch`, phase 2 reuses them -- the input is read twice in total instead of four times.
+template <class In>
+void device_scan_total(In in, u64 n, u64* scratch, u64* d_total, cudaStream_t st) {
+    if (n == 0) { cudaMemsetAsync(d_total, 0, sizeof(u64), st); return; }
+    u64 tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_tile_sums<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, scratch);
+    if (tiles <= (u64)SCAN_TILE * 64) k_scan_small<<<1, SCAN_THREADS, 0, st>>>(scratch, tiles, d_total);
+    else device_scan(ScanU64In{scratch}, ScanU64Out{scratch}, tiles, scratch + tiles + 1, d_total, st);
+}
+template <class In, class Out>
+void device_scan_finish(In in, Out out, u64 n, const u64* scratch, cudaStream_t st) {
+    if (n == 0) return;
+    u64 tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_apply<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, out, n, scratch);
+}
+
 }   // namespace pgb
