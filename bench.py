@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--sample-genome", type=int, default=2_500_000, help="cpu_baseline sample: sub-genome size at the same coverage")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--K", type=int, default=63, help="63 (headline, 63-mer flavour) or e.g. 127 (127-mer flavour, 256-bit keys; configs[3] shape)")
     return ap.parse_args()
 
 
@@ -175,6 +176,8 @@ def time_reference_pass1(cfg, workdir, threads, tag):
 
 def main():
     args = parse_args()
+    global K
+    K = args.K
     import torch
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -224,9 +227,9 @@ def main():
     t1, t2 = gen_pe_fastq_gpu(torch, dev, args.genome, n_pairs, seed=42)
     torch.cuda.synchronize()
     text_bytes = t1.numel() + t2.numel()
-    est_distinct = int(args.genome * 2.3) + 1_000_000
+    est_distinct = int(args.genome * (2.3 if K <= 63 else 3.6)) + 1_000_000   # ~K error k-mers per substitution
     slots = 1 << max(20, (int(est_distinct / world * 2.2 * float(os.environ.get('PGB200_BENCH_SLOTS_MULT', '1')))).bit_length())
-    eng = api.PregraphEngine(K=K, P=8, initG=0, max_rd_len=RD_LEN, device=local_rank, table_slots=slots, world=world, rank=rank,
+    eng = api.PregraphEngine(K=K, P=8, initG=0, flavour127=int(K > 63), max_rd_len=RD_LEN, device=local_rank, table_slots=slots, world=world, rank=rank,
                              verbose=int(os.environ.get("PGB200_VERBOSE", "0")))
     chunk = args.chunk_reads * REC_BYTES
 
@@ -323,15 +326,16 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     inst_per_rank = instances / world
-    achieved = inst_per_rank * 64 / (ins_ms / 1e3) / 1e9 if ins_ms > 0 else None
+    slot_bytes = 64 if K <= 63 else 128   # one slot sector read + written back
+    achieved = inst_per_rank * slot_bytes / (ins_ms / 1e3) / 1e9 if ins_ms > 0 else None
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_insert_traffic.json"))).get("dram_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_insert_traffic.json"))).get("dram_bytes_per_launch") if K == 63 and world == 1 else None
     except Exception:
         pass
-    roof = {"kernel": "k_chop_insert<2>" if world == 1 else "k_apply_tuples<2>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+    roof = {"kernel": ("k_chop_insert<%d>" if world == 1 else "k_apply_tuples<%d>") % (2 if K <= 63 else 4), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
             "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-            "algorithmic_bytes_per_instance": 64, "instances_per_step_per_gpu": inst_per_rank, "insert_kernel_ms_per_step": ins_ms}
+            "algorithmic_bytes_per_instance": slot_bytes, "instances_per_step_per_gpu": inst_per_rank, "insert_kernel_ms_per_step": ins_ms}
 
     cpu_b = None
     if not args.no_cpu_baseline:
@@ -346,7 +350,7 @@ def main():
             cpu_b = {"value": None, "error": str(ex)[:200]}
 
     print(json.dumps({
-        "metric": "distinct k-mers hashed/sec at K=63", "value": value, "unit": "distinct k-mers/s", "n_gpus": world, "steps": args.steps,
+        "metric": f"distinct k-mers hashed/sec at K={K}", "value": value, "unit": "distinct k-mers/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
         "config": {"workload": workload, "reads": 2 * n_pairs, "kmer_instances": int(instances), "distinct_kmers": int(distinct),

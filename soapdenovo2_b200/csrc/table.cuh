@@ -168,8 +168,9 @@ PG_D u64 table_find_or_claim<4>(const Table<4>& t, const Kmer<4>& k, bool* claim
             U128 old = atomicCAS(reinterpret_cast<U128*>(&s->key[0]), empty, want);
             if (old.a == EMPTY64 && old.b == EMPTY64) {
                 stcg128(&s->key[2], U128{k.w[2], k.w[3]});
-                __threadfence();
-                atomicExch(&s->key[0], k.w[0]);   // publish
+                // publish with a release store (orders the lower half before it) instead of __threadfence() + exchange: the fence
+                // compiles to MEMBAR.SC + CCTL.IVALL, paid by every new 256-bit key (a third of the instances at K=127)
+                asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&s->key[0]), "l"(k.w[0]) : "memory");
                 *claimed = true;
                 return idx;
             }
