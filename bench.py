@@ -8,8 +8,10 @@ table insert/count -> delow/mark-linear/kmerFreq sweeps) over the synthetic read
   value  : whole-job distinct k-mers / s with the FASTQ text already resident in HBM (device pointers through the C-ABI)
   e2e    : the same metric through the C-ABI with HOST (pinned) text buffers: H2D copies inside the timed region, plus a
            D2H read of the coverage histogram / statistics every step
-  roofline: k_chop_insert, HBM bound: algorithmic bytes = 64 B per k-mer instance (one 32 B slot sector read + written back),
-           SURVEY.md 8(d); time = CUDA events recorded by the engine on its own stream around every launch of that kernel
+  roofline: the insert, HBM bound: algorithmic bytes = 64 B per k-mer instance (one 32 B slot sector read + written back),
+           SURVEY.md 8(d); time = CUDA events recorded by the engine on its own stream around every launch of the insert kernels.
+           With the text resident in HBM the insert is the aggregated one (k_skm_part + k_skm_apply, soapdenovo2_b200/csrc/skm.cu:
+           super-k-mer buckets, one table update per DISTINCT k-mer); host text (e2e) and N>1 use the per-instance kernels
   cpu_baseline: the UNMODIFIED reference binary (oracle/_ref/SOAPdenovo-63mer pregraph, built from /root/reference by
            oracle/Makefile) timed on this box's host cores up to its "done hashing nodes" line, on a bounded sample
 N>1 (torchrun): the k-mer space is sharded by an owner hash; see DESIGN.md (e).
@@ -329,11 +331,14 @@ def main():
     slot_bytes = 64 if K <= 63 else 128   # one slot sector read + written back
     achieved = inst_per_rank * slot_bytes / (ins_ms / 1e3) / 1e9 if ins_ms > 0 else None
     traffic = None
+    aggregated = world == 1 and os.environ.get("PGB200_SKM", "auto") != "0"
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_insert_traffic.json"))).get("dram_bytes_per_launch") if K == 63 and world == 1 else None
+        tf = "r01_skm_apply_traffic.json" if aggregated else "r01_insert_traffic.json"
+        traffic = json.load(open(os.path.join(ROOT, "profiles", tf))).get("dram_bytes_per_launch") if K == 63 and world == 1 else None
     except Exception:
         pass
-    roof = {"kernel": ("k_chop_insert<%d>" if world == 1 else "k_apply_tuples<%d>") % (2 if K <= 63 else 4), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+    kname = "k_skm_apply<%d> (+ k_skm_part: aggregated insert)" if aggregated else ("k_chop_insert<%d>" if world == 1 else "k_apply_tuples<%d>")
+    roof = {"kernel": kname % (2 if K <= 63 else 4), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
             "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
             "algorithmic_bytes_per_instance": slot_bytes, "instances_per_step_per_gpu": inst_per_rank, "insert_kernel_ms_per_step": ins_ms}
 
@@ -355,6 +360,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload, "reads": 2 * n_pairs, "kmer_instances": int(instances), "distinct_kmers": int(distinct),
                    "instances_per_s": instances / (ms_step / 1e3), "table_slots_per_gpu": int(st.table_slots), "parallelism": f"k-mer space sharded over {world} GPU(s) by owner hash" + (", tuples stored straight into the owner GPU over NVLink by the bucketing kernel (PGB200_XCHG=nccl: NCCL all-to-all)" if world > 1 else ""),
+                   "insert_mode": ("value: aggregated (super-k-mer buckets, one table update per distinct k-mer); e2e: per-instance inserts overlapped with the H2D copies" if world == 1 and os.environ.get("PGB200_SKM", "auto") == "auto" else ("PGB200_SKM=" + os.environ.get("PGB200_SKM", "") if world == 1 else "per-instance tuples exchanged between owners")),
                    "l2_policy": "inputs (6.3 GB text, 17 GB table) are far larger than the 126 MB L2; the table is cleared every step"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_b}))
 

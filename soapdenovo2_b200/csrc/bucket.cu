@@ -332,6 +332,7 @@ void EngineT<NW>::sync_apply() {
 // price is 32 B written + read per instance for the tuple buffer.
 template <int NW>
 void EngineT<NW>::flush_batch() {
+    if (!skm_pending_.empty()) skm_flush();
     if (batch_gb_ <= 0 || prm_.world > 1 || pending_first_ >= chunks_.size()) return;   // only the single-GPU batch mode defers inserts
     settle_timing();
     read_counters();

@@ -4,6 +4,7 @@
 #include "engine.h"
 #include "kmer.cuh"
 #include "table.cuh"
+#include "skm.cuh"
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
@@ -139,6 +140,26 @@ public:
     u64 pending_bound_ = 0;      // upper bound of their k-mer instances
     void flush_batch();
     void apply_tuples(const u64* tuples, u64 n);
+    // aggregated pass 1 (skm.cu, single GPU): super-k-mer partition per chunk, shared-memory aggregation per bucket,
+    // one global update per DISTINCT k-mer
+    int skm_mode_ = -1;   // -1: aggregated for device-resident text, per-chunk inserts for host text; 0 / 1: forced (PGB200_SKM)
+    SkmGeom skm_geom_;
+    DevBuf skm_inst_, skm_cursor_, skm_desc_, skm_side_;   // k-mers per bucket (pending chunks), scatter cursors, chunk descriptors + bucket counter
+    struct SkmPending { size_t chunk = 0; u32* segoff = nullptr; u64* recs = nullptr; u64 n_recs = 0; };
+    std::vector<SkmPending> skm_pending_;
+    bool skm_unscattered_ = false;               // the last pending chunk is counted but its records are not written yet
+    u64 skm_pending_recs_ = 0, skm_prev_total_ = 0;
+    std::vector<std::pair<void*, size_t>> skm_blocks_;   // bump-allocated scratch (segment offsets, records), reused after every flush
+    size_t skm_blk_ = 0, skm_used_ = 0;
+    cudaEvent_t ev_skm_[2] = {nullptr, nullptr};
+    int skm_part_threads_ = 128;
+    void* skm_alloc(size_t bytes);
+    void skm_init();
+    void skm_count_chunk(size_t ci);
+    void skm_scatter_last(u64 total);
+    void skm_flush();
+    void skm_reset();
+    void skm_release();
 public:
     // multi-GPU exchange surface (C-ABI: pgb200_exchange_*)
     static constexpr int tuple_words() { return NW == 2 ? 4 : 8; }

@@ -69,19 +69,29 @@ PG_HD Kmer<NW> kshr2(const Kmer<NW>& a) {
     for (int i = NW - 1; i >= 0; i--) r.w[i] = (a.w[i] >> 2) | (i > 0 ? (a.w[i - 1] << 62) : 0ull);
     return r;
 }
-// generic right shift by `s` bits, 0 <= s < 64*NW
-template <int NW>
-PG_HD Kmer<NW> kshr(const Kmer<NW>& a, int s) {
+// generic right shift by `s` bits, 0 <= s < 64*NW.  The word offset is dispatched through a switch so that every w[] index is a
+// compile-time constant: a dynamically indexed w[] lives in local memory on the GPU (LDL/STL in every reverse complement), and
+// the shift amount is uniform (it depends on K only), so the switch is a uniform branch.
+template <int NW, int WS>
+PG_HD Kmer<NW> kshr_words(const Kmer<NW>& a, int bs) {
     Kmer<NW> r;
-    int ws = s >> 6, bs = s & 63;
 #pragma unroll
     for (int i = NW - 1; i >= 0; i--) {
-        int src = i - ws;
-        u64 lo = src >= 0 ? a.w[src] : 0ull;
-        u64 hi = src - 1 >= 0 ? a.w[src - 1] : 0ull;
+        const u64 lo = i - WS >= 0 ? a.w[i - WS >= 0 ? i - WS : 0] : 0ull;
+        const u64 hi = i - WS - 1 >= 0 ? a.w[i - WS - 1 >= 0 ? i - WS - 1 : 0] : 0ull;
         r.w[i] = bs ? ((lo >> bs) | (hi << (64 - bs))) : lo;
     }
     return r;
+}
+template <int NW>
+PG_HD Kmer<NW> kshr(const Kmer<NW>& a, int s) {
+    const int bs = s & 63;
+    switch (s >> 6) {
+        case 0: return kshr_words<NW, 0>(a, bs);
+        case 1: return kshr_words<NW, 1>(a, bs);
+        case 2: return kshr_words<NW, (NW > 2 ? 2 : 0)>(a, bs);
+        default: return kshr_words<NW, (NW > 3 ? 3 : 0)>(a, bs);
+    }
 }
 
 // Per-K constants (WORDFILTER = createFilter(K), kmer.c:738-758)

@@ -451,6 +451,11 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     read_counters();
     u64 n_lines = h_cnt_[C_MISC0];
     const u64 have_distinct = h_cnt_[C_DISTINCT];
+    // aggregated pass 1 (skm.cu) for text that is already resident in HBM; text arriving over PCIe is inserted chunk by chunk
+    // (k_chop_insert) because those inserts hide completely under the next chunk's copy, while the aggregation would only start
+    // after the last one.  PGB200_SKM=0/1 forces one path.
+    const bool use_skm = prm_.world <= 1 && (skm_mode_ > 0 || (skm_mode_ < 0 && on_device));
+    if (skm_unscattered_) skm_prev_total_ = h_cnt_[C_MISC1];   // record count of the previous aggregated chunk (k_skm_offsets)
     // a final line without '\n' still counts (the reference's FASTQ path tolerates it; its FASTA path does not)
     unsigned char lastc = *h_last;
     bool open_tail = lastc != '\n';
@@ -491,7 +496,10 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     PG_CUDA(cudaEventRecord(ev_[1], st_));
     // table capacity for the worst case of this chunk (host-side bound: no sync; growth itself syncs when it happens)
     if (xchg_fused_) create_table_if_needed();   // an apply may be in flight on the other stream: growth is decided in xchg_apply
-    else {
+    else if (use_skm) {
+        create_table_if_needed();                 // growth is decided per bucket range in skm_flush
+        if (skm_pending_.size() >= 64) { skm_scatter_last(skm_prev_total_); skm_flush(); }
+    } else {
         int per_read = maxlen - prm_.K + 1;
         ensure_table_bound(have_distinct, per_read > 0 ? n_rec * (u64)per_read : 0);
     }
@@ -500,6 +508,9 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     PG_CUDA(cudaEventRecord(ev_[2], st_));
     if (prm_.world > 1) {
         bucket_chunk(ch);                       // tuples stay in the exchange buffer: caller runs the all-to-all
+    } else if (use_skm) {
+        skm_scatter_last(skm_prev_total_);      // records of the previous chunk (its count arrived with this chunk's host sync)
+        skm_count_chunk(chunks_.size() - 1);
     } else if (batch_gb_ > 0) {
         int per_read = maxlen - prm_.K + 1;
         pending_bound_ += per_read > 0 ? n_rec * (u64)per_read : 0;
@@ -568,6 +579,7 @@ void EngineT<NW>::reset_pass1() {
     settle_timing();
     sync();
     chunks_.clear();
+    skm_reset();
     pending_first_ = 0;
     pending_bound_ = 0;
     // keep the first arena block for the next pass, release the rest
@@ -652,6 +664,7 @@ EngineT<NW>::EngineT(const PgParams& p) : prm_(p) {
     if (const char* g = getenv("PGB200_INSERT_SM")) insert_sm_ = atoi(g);
     if (const char* g = getenv("PGB200_DBG_INSERT")) dbg_insert_ = atoi(g);
     if (const char* g = getenv("PGB200_BATCH_GB")) batch_gb_ = atof(g);
+    if (const char* g = getenv("PGB200_SKM")) skm_mode_ = atoi(g) ? 1 : 0;
     if (l2gran_mode_ == 1) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     kp_ = make_kparams<NW>(p.K);
     PG_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
@@ -673,6 +686,7 @@ template <int NW>
 EngineT<NW>::~EngineT() {
     cudaStreamSynchronize(st_);
     for (auto& a : arena_) cudaFree(a.first);
+    skm_release();
     if (d_cnt_) cudaFree(d_cnt_);
     if (h_cnt_) cudaFreeHost(h_cnt_);
     for (auto& e : ev_) if (e) cudaEventDestroy(e);

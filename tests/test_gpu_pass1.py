@@ -15,6 +15,15 @@ def _build():
     util.build_oracle()
 
 
+@pytest.fixture(params=["direct", "aggregated"], autouse=True)
+def _insert_mode(request, monkeypatch):
+    """Every case runs twice: per-instance inserts (k_chop_insert) and the aggregated pass 1 (super-k-mer buckets, skm.cu)."""
+    if request.param == "aggregated":
+        monkeypatch.setenv("PGB200_SKM", "1")
+    else:
+        monkeypatch.delenv("PGB200_SKM", raising=False)
+
+
 def _feed_cfg_files(eng, files, fastq, stride=1, base=0, **kw):
     n = 0
     for i, fn in enumerate(files):
