@@ -147,15 +147,21 @@ struct SmemTable {
     u64* rnk;
     unsigned short* list;
     u32* count;
-    __device__ __forceinline__ bool insert(const Table<NW>& tab, const Kmer<NW>& k, unsigned left, unsigned right, u64 rank) const {
-        u32 idx = skm_slot_hash(k, SKM_LOG2_SLOTS);
+    // Two phases with a warp barrier between them (the caller's __syncwarp over the lanes that have an instance): first every lane
+    // finds or claims its slot (lanes differ only in the number of probes), then the lanes that found an existing key apply their
+    // instance TOGETHER.  Without the barrier the lanes that match on their first probe leave the loop and run the (long) update
+    // on their own while the others keep probing (ncu: the update code ran twice per step with 9 active lanes); a formulation of
+    // the loop alone does not help, ptxas produces the same code for all of them.
+    // find(): 1 = key present at idx, 2 = claimed by this lane (first instance already recorded), 3 = no room (caller spills)
+    __device__ __forceinline__ int find(const Table<NW>& tab, const Kmer<NW>& k, unsigned left, unsigned right, u64 rank, u32& idx) const {
+        idx = skm_slot_hash(k, SKM_LOG2_SLOTS);
         volatile u64* vkey = key;
         volatile u64* vpay = pay;
         volatile u64* vrnk = rnk;
-        for (int probe = 0; probe < SKM_SLOTS; probe++, idx = (idx + 1) & (SKM_SLOTS - 1)) {
+        for (int probe = 0; probe < SKM_SLOTS; probe++) {
             u64 k0 = vkey[idx];
             if (k0 == EMPTY64) {
-                if (*(volatile u32*)count >= (u32)SKM_SOFT_LIMIT) return false;
+                if (*(volatile u32*)count >= (u32)SKM_SOFT_LIMIT) return 3;
                 u64 old = atomicCAS(&key[idx], EMPTY64, k.w[0] | BUSY_BIT);
                 if (old == EMPTY64) {
 #pragma unroll
@@ -167,28 +173,33 @@ struct SmemTable {
                     const u32 n = atomicAdd(count, 1u);
                     list[n] = (unsigned short)idx;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(tab.slots + (table_hash(k) & tab.mask)));
-                    return true;
+                    return 2;
                 }
                 k0 = old;
             }
-            if ((k0 & ~BUSY_BIT) != k.w[0]) continue;
-            while (k0 & BUSY_BIT) k0 = vkey[idx];
-            bool same = true;
+            if ((k0 & ~BUSY_BIT) == k.w[0]) {
+                while (k0 & BUSY_BIT) k0 = vkey[idx];
+                bool same = true;
 #pragma unroll
-            for (int w = 1; w < NW; w++) same = same && vkey[w * SKM_SLOTS + idx] == k.w[w];
-            if (!same) continue;
-            u64 cur = vpay[idx];
-            for (;;) {
-                u64 nxt = payload_apply(cur, left, right);
-                if (nxt == cur) break;
-                u64 old = atomicCAS(&pay[idx], cur, nxt);
-                if (old == cur) break;
-                cur = old;
+                for (int w = 1; w < NW; w++) same = same && vkey[w * SKM_SLOTS + idx] == k.w[w];
+                if (same) return 1;
             }
-            if (rank < vrnk[idx]) atomicMin(&rnk[idx], rank);
-            return true;
+            idx = (idx + 1) & (SKM_SLOTS - 1);
         }
-        return false;
+        return 3;
+    }
+    __device__ __forceinline__ void apply(u32 idx, unsigned left, unsigned right, u64 rank) const {
+        volatile u64* vpay = pay;
+        volatile u64* vrnk = rnk;
+        u64 cur = vpay[idx];
+        for (;;) {
+            u64 nxt = payload_apply(cur, left, right);
+            if (nxt == cur) break;
+            u64 old = atomicCAS(&pay[idx], cur, nxt);
+            if (old == cur) break;
+            cur = old;
+        }
+        if (rank < vrnk[idx]) atomicMin(&rnk[idx], rank);
     }
 };
 
@@ -292,16 +303,24 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply(Table<NW> tab, 
                 skm_load_words<NW>(s_chunk[c_nxt].words + (u64)skm_read(rec_nxt) * W64, W64, skm_start(rec_nxt) + t, nbuf);
             if (g + 2 * SKM_HALF_WARPS < total) rec_nn = next_rec(g + 2 * SKM_HALF_WARPS, c_nn);
             const int n = skm_count(rec);
-            if (act && t < n) {
+            const bool has = act && t < n;
+            const unsigned has_mask = __ballot_sync(0xffffffffu, has);   // all 32 lanes are together here
+            if (has) {
                 const int j = skm_start(rec) + t;
                 const SkmInst<NW> in = skm_instance<NW>(kp, buf, j, !(skm_last(rec) && t == n - 1));
                 const SkmChunkDev& ch = s_chunk[c_cur];
                 const u64 rank = ((ch.ord_base + (u64)skm_read(rec) * ch.ord_stride) << 16) | (u64)j;
                 if (dbg >= 2) { my_spill += skm_slot_hash(in.canon, SKM_LOG2_SLOTS) + in.left + in.right; }   // PGB200_SKM_DBG=2: no table work at all (timing only)
-                else if (!st.insert(tab, in.canon, in.left, in.right, rank)) {
-                    // bucket holds more distinct k-mers than the shared-memory table: this instance goes to HBM directly (same result)
-                    my_new += table_insert(tab, in.canon, in.left, in.right, rank);
-                    my_spill++;
+                else {
+                    u32 slot;
+                    const int state = st.find(tab, in.canon, in.left, in.right, rank, slot);
+                    __syncwarp(has_mask);   // the lanes re-join before the counter update (see SmemTable)
+                    if (state == 1) st.apply(slot, in.left, in.right, rank);
+                    else if (state == 3) {
+                        // bucket holds more distinct k-mers than the shared-memory table: this instance goes to HBM directly (same result)
+                        my_new += table_insert(tab, in.canon, in.left, in.right, rank);
+                        my_spill++;
+                    }
                 }
             }
             rec = rec_nxt; c_cur = c_nxt;
