@@ -48,12 +48,13 @@ typedef struct pgb200_params {
     int max_rd_len;   /* maxReadLen4all (config max_rd_len, default 100)                                         */
     uint64_t table_slots; /* GPU k-mer table capacity hint (0 = derive from -a / grow on demand)                */
     int verbose;
-    int world, rank;  /* k-mer space sharding across GPUs: this engine keeps keys whose owner hash % world == rank */
+    int world, rank;  /* k-mer space sharding across GPUs: this engine owns bucket range `rank` of `world` (see pgb200_xchg_*) */
 } pgb200_params;
 
 typedef struct pgb200_pass1_stats {
     uint64_t records, reads_kept, instances, distinct, table_slots, launches;
-    double ms_decode, ms_insert;
+    double ms_decode, ms_insert;   /* CUDA-event times; ms_insert = partition + aggregation */
+    double ms_apply;               /* the aggregation launches alone */
 } pgb200_pass1_stats;
 
 const char *pgb200_last_error(void);
@@ -72,26 +73,25 @@ int pgb200_feed_text(pgb200_engine *e, const char *text, size_t nbytes, int on_d
                      uint64_t ord_stride, int reverse_seq, int maxlen);
 uint64_t pgb200_last_chunk_records(pgb200_engine *e);
 
-/* Multi-GPU (params.world > 1): the k-mer space is sharded by an owner hash.  pgb200_feed_text then only decodes the chunk and
- * groups its (k-mer, links, rank) tuples by owner rank in a device buffer; the caller moves range o to rank o (one bucketed
- * all-to-all per round, e.g. NCCL via torch.distributed.all_to_all_single) and hands what it received to pgb200_apply_tuples.
+/* Multi-GPU (params.world > 1).  Pass 1 is aggregated per minimizer bucket (super-k-mer records, csrc/skm.cuh); engine `rank` owns a
+ * contiguous range of the buckets.  Every engine has an ARENA that all engines of the job store records into: pgb200_feed_text
+ * decodes the chunk, partitions it and stores every record STRAIGHT INTO ITS OWNER'S ARENA (peer stores over NVLink from the
+ * partition kernel; senders have private regions, so no negotiation and no library collective on the data path).
  * This replaces the reference's "every thread scans the whole batch and keeps hash % thrd_num == id" (prlHashReads.c:79-90).
- * ranges has world+1 entries (tuple indices); a tuple is tuple_bytes bytes (32 for K <= 63, 64 for K <= 127).            */
-const void *pgb200_exchange_buffer(pgb200_engine *e, uint64_t *ranges, int *tuple_bytes);
-int pgb200_exchange_clear(pgb200_engine *e);
-int pgb200_apply_tuples(pgb200_engine *e, const void *dev_tuples, uint64_t n_tuples);
-
-/* Fused exchange (no library collective on the data path): every rank owns two receive buffers; the other ranks map them with
- * CUDA IPC and the scatter kernel stores each tuple STRAIGHT into its owner's buffer over NVLink while it is still chopping the
- * next reads.  Protocol per round: feed_text (decode + count) -> xchg_counts -> [callers all-gather the world x world count
- * matrix: 8 bytes per pair] -> xchg_scatter(buf, base) with base[o] = sum of the counts of lower ranks for owner o ->
- * [barrier] -> xchg_apply(buf, sum of counts for me).  handle64 = the 64-byte cudaIpcMemHandle_t of buffer `buf`.          */
-int pgb200_xchg_setup(pgb200_engine *e, uint64_t cap_tuples);
-int pgb200_xchg_export(pgb200_engine *e, int buf, void *handle64);
-int pgb200_xchg_import(pgb200_engine *e, int peer, int buf, const void *handle64);
-int pgb200_xchg_counts(pgb200_engine *e, uint64_t *counts);
-int pgb200_xchg_scatter(pgb200_engine *e, int buf, const uint64_t *base);
-int pgb200_xchg_apply(pgb200_engine *e, int buf, uint64_t n_tuples);
+ *   setup, once:   pgb200_xchg_setup(cap)  ->  exchange arenas: other processes  pgb200_xchg_export / pgb200_xchg_import (64-byte
+ *                  cudaIpcMemHandle_t), same process  pgb200_xchg_base / pgb200_xchg_import_ptr (peer access)
+ *   per epoch:     pgb200_feed_text ... (any number of chunks, each engine its own)  ->  pgb200_xchg_fence  ->  [caller: barrier over
+ *                  all engines]  ->  pgb200_flush  (aggregates what this engine received into its table)
+ * Arenas are double-buffered by epoch: an engine may start feeding the next epoch while others still aggregate.
+ * world == 1 needs none of this (the engine sets up a private arena and flushes by itself).
+ * cap_records = arena capacity in records (32 B for K <= 63, 48 B for K <= 127), summed over the `world` senders.            */
+int pgb200_xchg_setup(pgb200_engine *e, uint64_t cap_records);
+int pgb200_xchg_export(pgb200_engine *e, void *handle64);
+int pgb200_xchg_import(pgb200_engine *e, int peer, const void *handle64);
+void *pgb200_xchg_base(pgb200_engine *e);
+int pgb200_xchg_import_ptr(pgb200_engine *e, int peer, int peer_device, void *base);
+int pgb200_xchg_fence(pgb200_engine *e);
+int pgb200_flush(pgb200_engine *e);
 int pgb200_finish_pass1(pgb200_engine *e, pgb200_pass1_stats *st);
 int pgb200_reset_pass1(pgb200_engine *e);
 /* delow (-d) + mark linear + coverage histogram: hist[c] = number of k-mers with coverage c (the .kmerFreq lines are hist[1..255]) */

@@ -15,8 +15,9 @@ BIN127 = os.path.join(_HERE, "bin", "pregraph-b200-127mer")
 
 EXPORTS = [
     "pgb200_last_error", "pgb200_default_params", "pgb200_create", "pgb200_destroy", "pgb200_host_alloc", "pgb200_host_free",
-    "pgb200_feed_text", "pgb200_last_chunk_records", "pgb200_exchange_buffer", "pgb200_exchange_clear", "pgb200_apply_tuples",
-    "pgb200_xchg_setup", "pgb200_xchg_export", "pgb200_xchg_import", "pgb200_xchg_counts", "pgb200_xchg_scatter", "pgb200_xchg_apply", "pgb200_finish_pass1", "pgb200_reset_pass1", "pgb200_sweeps",
+    "pgb200_feed_text", "pgb200_last_chunk_records",
+    "pgb200_xchg_setup", "pgb200_xchg_export", "pgb200_xchg_import", "pgb200_xchg_base", "pgb200_xchg_import_ptr", "pgb200_xchg_fence", "pgb200_flush",
+    "pgb200_finish_pass1", "pgb200_reset_pass1", "pgb200_sweeps",
     "pgb200_build_layout", "pgb200_node_count", "pgb200_dump_nodes", "pgb200_remove_tips", "pgb200_kmer2edges",
     "pgb200_read2edge", "pgb200_output_vertex", "pgb200_plan_files", "pgb200_pregraph_main", "call_pregraph",
 ]
@@ -30,7 +31,8 @@ class Params(C.Structure):
 
 class Pass1Stats(C.Structure):
     _fields_ = [("records", C.c_uint64), ("reads_kept", C.c_uint64), ("instances", C.c_uint64), ("distinct", C.c_uint64),
-                ("table_slots", C.c_uint64), ("launches", C.c_uint64), ("ms_decode", C.c_double), ("ms_insert", C.c_double)]
+                ("table_slots", C.c_uint64), ("launches", C.c_uint64), ("ms_decode", C.c_double), ("ms_insert", C.c_double),
+                ("ms_apply", C.c_double)]
 
 
 class GraphStats(C.Structure):
@@ -58,16 +60,14 @@ def load():
     lib.pgb200_feed_text.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int]
     lib.pgb200_last_chunk_records.restype = C.c_uint64
     lib.pgb200_last_chunk_records.argtypes = [C.c_void_p]
-    lib.pgb200_exchange_buffer.restype = C.c_void_p
-    lib.pgb200_exchange_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
-    lib.pgb200_exchange_clear.argtypes = [C.c_void_p]
-    lib.pgb200_apply_tuples.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     lib.pgb200_xchg_setup.argtypes = [C.c_void_p, C.c_uint64]
-    lib.pgb200_xchg_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
-    lib.pgb200_xchg_import.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
-    lib.pgb200_xchg_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
-    lib.pgb200_xchg_scatter.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
-    lib.pgb200_xchg_apply.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+    lib.pgb200_xchg_export.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pgb200_xchg_import.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.pgb200_xchg_base.restype = C.c_void_p
+    lib.pgb200_xchg_base.argtypes = [C.c_void_p]
+    lib.pgb200_xchg_import_ptr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.pgb200_xchg_fence.argtypes = [C.c_void_p]
+    lib.pgb200_flush.argtypes = [C.c_void_p]
     lib.pgb200_finish_pass1.argtypes = [C.c_void_p, C.POINTER(Pass1Stats)]
     lib.pgb200_reset_pass1.argtypes = [C.c_void_p]
     lib.pgb200_sweeps.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -128,45 +128,30 @@ class PregraphEngine:
                                            maxlen if maxlen is not None else self.params.max_rd_len))
         return self.lib.pgb200_last_chunk_records(self.h)
 
-    def exchange_buffer(self):
-        """-> (device pointer, [world+1] tuple range starts, bytes per tuple) of the owner-grouped tuples of the last fed chunk."""
-        w = max(1, self.params.world)
-        ranges = (C.c_uint64 * (w + 1))()
-        tb = C.c_int()
-        ptr = self.lib.pgb200_exchange_buffer(self.h, ranges, C.byref(tb))
-        return ptr or 0, list(ranges), tb.value
+    # ---- multi-GPU record exchange (peer stores over NVLink): see include/pregraph_b200.h
+    def xchg_setup(self, cap_records):
+        self._ck(self.lib.pgb200_xchg_setup(self.h, cap_records))
 
-    def exchange_clear(self):
-        self._ck(self.lib.pgb200_exchange_clear(self.h))
-
-    def apply_tuples(self, dev_ptr, n_tuples):
-        self._ck(self.lib.pgb200_apply_tuples(self.h, C.c_void_p(int(dev_ptr)), n_tuples))
-
-    # ---- fused exchange (peer stores over NVLink): see include/pregraph_b200.h
-    def xchg_setup(self, cap_tuples):
-        self._ck(self.lib.pgb200_xchg_setup(self.h, cap_tuples))
-
-    def xchg_export(self, buf) -> bytes:
+    def xchg_export(self) -> bytes:
         h = C.create_string_buffer(64)
-        self._ck(self.lib.pgb200_xchg_export(self.h, buf, h))
+        self._ck(self.lib.pgb200_xchg_export(self.h, h))
         return h.raw
 
-    def xchg_import(self, peer, buf, handle: bytes):
+    def xchg_import(self, peer, handle: bytes):
         h = C.create_string_buffer(handle, 64)
-        self._ck(self.lib.pgb200_xchg_import(self.h, peer, buf, h))
+        self._ck(self.lib.pgb200_xchg_import(self.h, peer, h))
 
-    def xchg_counts(self):
-        w = max(1, self.params.world)
-        c = (C.c_uint64 * w)()
-        self._ck(self.lib.pgb200_xchg_counts(self.h, c))
-        return list(c)
+    def xchg_base(self) -> int:
+        return self.lib.pgb200_xchg_base(self.h) or 0
 
-    def xchg_scatter(self, buf, base):
-        b = (C.c_uint64 * len(base))(*base)
-        self._ck(self.lib.pgb200_xchg_scatter(self.h, buf, b))
+    def xchg_import_ptr(self, peer, peer_device, base):
+        self._ck(self.lib.pgb200_xchg_import_ptr(self.h, peer, peer_device, C.c_void_p(int(base))))
 
-    def xchg_apply(self, buf, n):
-        self._ck(self.lib.pgb200_xchg_apply(self.h, buf, n))
+    def xchg_fence(self):
+        self._ck(self.lib.pgb200_xchg_fence(self.h))
+
+    def flush(self):
+        self._ck(self.lib.pgb200_flush(self.h))
 
     def finish_pass1(self) -> Pass1Stats:
         st = Pass1Stats()

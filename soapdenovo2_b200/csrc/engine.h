@@ -19,7 +19,7 @@ struct PgParams {
     int max_rd_len = 100;    // maxReadLen4all
     uint64_t table_slots = 0;   // capacity hint for the GPU table (rounded up to a power of two); 0 = derive
     int verbose = 0;
-    // multi-GPU sharding of the k-mer space (rank r owns keys with owner_hash % world == r)
+    // multi-GPU sharding of the k-mer space (rank r owns a contiguous range of minimizer buckets, skm.cuh)
     int world = 1, rank = 0;
 };
 
@@ -29,8 +29,9 @@ struct Pass1Stats {
     uint64_t instances = 0;      // "kmer(s) in reads"
     uint64_t distinct = 0;       // "node(s) allocated"
     uint64_t table_slots = 0;
-    double ms_decode = 0, ms_insert = 0;   // CUDA-event times accumulated over chunks
+    double ms_decode = 0, ms_insert = 0;   // CUDA-event times accumulated over chunks (ms_insert includes ms_apply)
     uint64_t launches = 0;
+    double ms_apply = 0;                   // the aggregation launches (k_skm_apply) alone
 };
 
 struct SweepStats {
@@ -67,18 +68,16 @@ public:
     virtual void feed_text(const char* text, size_t nbytes, bool on_device, int fastq, uint64_t ord_base, uint64_t ord_stride,
                            int reverse_seq, int maxlen) = 0;
     virtual uint64_t last_chunk_records() const = 0;
-    // multi-GPU (world > 1): after feed_text the chunk's tuples sit in an exchange buffer grouped by owner rank.
-    // ranges[o]..ranges[o+1] (in tuples) belong to owner o; tuple_bytes per tuple.  apply_received() inserts tuples this rank owns.
-    virtual const void* exchange_buffer(uint64_t* ranges /*world+1*/, int* tuple_bytes) = 0;
-    virtual void exchange_clear() = 0;
-    virtual void apply_received(const void* dev_tuples, uint64_t n) = 0;
-    // fused exchange (peer stores over NVLink instead of a library all-to-all): see include/pregraph_b200.h, pgb200_xchg_*
-    virtual void xchg_setup(uint64_t cap_tuples) = 0;
-    virtual void xchg_export(int buf, void* handle64) = 0;
-    virtual void xchg_import(int peer, int buf, const void* handle64) = 0;
-    virtual void xchg_counts(uint64_t* counts) = 0;
-    virtual void xchg_scatter(int buf, const uint64_t* base) = 0;
-    virtual void xchg_apply(int buf, uint64_t n) = 0;
+    // Aggregated pass 1 / multi-GPU exchange (skm.cu).  Every engine owns an arena that all engines of the job (itself included)
+    // store super-k-mer records into; rank r aggregates the buckets it owns.  world == 1 needs none of these calls.
+    //   xchg_setup -> [exchange handles / base pointers, xchg_import*] -> feed_text ... -> xchg_fence -> [barrier] -> flush
+    virtual void xchg_setup(uint64_t cap_records) = 0;                 // arena capacity in records, summed over senders
+    virtual void xchg_export(void* handle64) = 0;                      // CUDA IPC handle of the arena (other processes)
+    virtual void xchg_import(int peer, const void* handle64) = 0;
+    virtual void* xchg_base() = 0;                                      // arena base pointer (other GPUs of the same process)
+    virtual void xchg_import_ptr(int peer, int peer_device, void* base) = 0;
+    virtual void xchg_fence() = 0;    // every record this engine produced so far has reached its owner
+    virtual void flush() = 0;         // aggregate the fenced records into the table (after every engine has fenced)
     virtual void finish_pass1(Pass1Stats* st) = 0;
     virtual void reset_pass1() = 0;   // drop reads + table (bench: repeat the step)
     virtual void sweeps(SweepStats* st) = 0;            // delow + mark linear + kmerFreq histogram
@@ -90,6 +89,7 @@ public:
     virtual void build_edges(EdgeStats* st, std::string* edge_text) = 0;   // uncompressed .edge text, in edge order
     virtual void pass2(Pass2Stats* st, std::string* prearc_text, std::string* path_bin, std::string* mark_text) = 0;
     virtual void vertices(std::string* vertex_text, uint64_t* n_vertex) = 0;
+    virtual uint64_t num_ed() const = 0;   // edge_c incl. twins, as of build_edges (the EDGEs line of .preGraphBasic)
 };
 
 IEngine* make_engine(const PgParams& p);   // picks 128- or 256-bit keys from K; throws std::runtime_error on CUDA errors

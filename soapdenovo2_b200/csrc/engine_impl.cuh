@@ -1,4 +1,4 @@
-// engine_impl.cuh -- EngineT<NW>: device state + phase methods; the methods are defined across decode.cu, pass1.cu,
+// engine_impl.cuh -- EngineT<NW>: device state + phase methods; the methods are defined across decode.cu, pass1.cu, skm.cu,
 // layout.cu, tips.cu, edges.cu, pass2.cu and explicitly instantiated for NW = 2 (K <= 63) and NW = 4 (K <= 127).
 #pragma once
 #include "engine.h"
@@ -52,7 +52,9 @@ struct ReadChunk {
     u64 ord_base = 0, ord_stride = 1;
 };
 
-enum Counter { C_DISTINCT = 0, C_INSTANCES, C_KEPT, C_LINEAR, C_REMOVED, C_MISC0, C_MISC1, C_MISC2, C_COUNT = 16 };
+// C_RESERVED, C_DEFER, C_MAXU must stay consecutive (skm_flush resets them with one copy)
+enum Counter { C_DISTINCT = 0, C_INSTANCES, C_KEPT, C_LINEAR, C_REMOVED, C_MISC0, C_MISC1, C_MISC2, C_BADFMT, C_XERR, C_XUSED, C_RESERVED, C_DEFER, C_MAXU,
+               C_COUNT = 16 };
 
 template <int NW>
 class EngineT : public IEngine {
@@ -73,6 +75,7 @@ public:
     void build_edges(EdgeStats* st, std::string* edge_text) override;
     void pass2(Pass2Stats* st, std::string* prearc_text, std::string* path_bin, std::string* mark_text) override;
     void vertices(std::string* vertex_text, uint64_t* n_vertex) override;
+    uint64_t num_ed() const override { return num_ed_; }
 
     // ---- state
     PgParams prm_;
@@ -80,10 +83,6 @@ public:
     cudaStream_t st_ = nullptr;
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     int W64_ = 0;   // packed words per read
-    int insert_sm_ = 0;     // PGB200_INSERT_SM=1: per-lane state-machine variant of the insert (K <= 63); measured slower, kept for the record
-    int dbg_insert_ = 0;    // PGB200_DBG_INSERT: cost-decomposition variants of k_chop_insert (profiling only)
-    int l2gran_mode_ = 0;   // PGB200_L2GRAN: 0 default, 1 = 32 B globally, 2 = 32 B only around k_chop_insert
-
     std::vector<ReadChunk> chunks_;
     uint64_t last_records_ = 0, total_records_ = 0;
     Pass1Stats p1_;
@@ -113,82 +112,43 @@ public:
     DevBuf patch_buf_;          // (K+1)-mer patch table
     u64 patch_mask_ = 0;
 
-    // bucketed insert path (bucket.cu): tuples {key words, meta} grouped by (owner GPU, table region)
-    int bucket_mode_ = 0;       // PGB200_BUCKET=1: single-GPU inserts also go through the bucketed (region-sorted) path
-    DevBuf tuple_bufs_[2], tilecnt_buf_, tileoff_buf_;   // two tuple buffers: chunk i+1 is bucketed while chunk i is on the wire
-    int tuple_flip_ = 0;
-    DevBuf& tuple_buf() { return tuple_bufs_[tuple_flip_]; }
-    u64 n_tuples_ = 0;          // tuples currently in tuple_buf_
-    int n_buckets_ = 0, region_bits_ = 0;
-    std::vector<u64> owner_start_;   // [world + 1] tuple offsets of each owner's range in tuple_buf_
-    void bucket_chunk(const ReadChunk& ch);
-    void bucket_chunks(const ReadChunk* chs, size_t n, u64 region_bytes, int rpt, bool scatter_now);
-    void bucket_scatter(const ReadChunk* chs, size_t n, u64* tuples, const void* peers);
-    struct BucketGeom { int region_shift = 0, rb = 0, NB = 0, rpt = 1; std::vector<u64> tile0; } bk_;
-    // fused exchange: receive buffers other ranks store into directly (CUDA IPC peer mappings over NVLink)
-    bool xchg_fused_ = false;
-    u64 xchg_cap_ = 0;
-    DevBuf xchg_recv_[2], xchg_dst_;
-    std::vector<void*> xchg_peer_[2];
-    cudaStream_t st_apply_ = nullptr;
-    cudaEvent_t ev_apply_[2] = {nullptr, nullptr};
-    bool apply_inflight_ = false;
-    void sync_apply();
-    // batch mode (PGB200_BATCH_GB > 0): inserts are deferred and done region-sorted over many chunks at once
-    double batch_gb_ = 0;
-    size_t pending_first_ = 0;   // chunks_[pending_first_..) are decoded but not inserted yet
-    u64 pending_bound_ = 0;      // upper bound of their k-mer instances
-    void flush_batch();
-    void apply_tuples(const u64* tuples, u64 n);
-    // aggregated pass 1 (skm.cu, single GPU): super-k-mer partition per chunk, shared-memory aggregation per bucket,
-    // one global update per DISTINCT k-mer
-    int skm_mode_ = -1;   // -1: aggregated for device-resident text, per-chunk inserts for host text; 0 / 1: forced (PGB200_SKM)
+    // pass 1, per-instance insert (pass1.cu): PGB200_SKM=0, single GPU only -- the second exact path the parity tests compare with
+    void chop_insert_chunk(const ReadChunk& ch);
+    void check_format_counter();
+    // pass 1, aggregated (skm.cu): super-k-mer records scattered into the owners' arenas, one table update per DISTINCT k-mer
+    int skm_mode_ = -1;          // -1 / 1: aggregated (default), 0: per-instance inserts (PGB200_SKM, world == 1 only)
+    int skm_flush_every_ = -1;   // single GPU: aggregate every n chunks (-1: host text 4, device text only when the arena is full)
     SkmGeom skm_geom_;
-    DevBuf skm_inst_, skm_cursor_, skm_desc_, skm_side_;   // k-mers per bucket (pending chunks), scatter cursors, chunk descriptors + bucket counter
-    struct SkmPending { size_t chunk = 0; u32* segoff = nullptr; u64* recs = nullptr; u64 n_recs = 0; };
-    std::vector<SkmPending> skm_pending_;
-    bool skm_unscattered_ = false;               // the last pending chunk is counted but its records are not written yet
-    u64 skm_pending_recs_ = 0, skm_prev_total_ = 0;
-    std::vector<std::pair<void*, size_t>> skm_blocks_;   // bump-allocated scratch (segment offsets, records), reused after every flush
-    size_t skm_blk_ = 0, skm_used_ = 0;
+    u32 skm_own_lo_ = 0, skm_own_hi_ = 0;
+    int skm_own_shift_ = -1;
+    DevBuf skm_cnt_, skm_segoff_, skm_cursor_, skm_scan_, skm_side_, skm_misc_;
     cudaEvent_t ev_skm_[2] = {nullptr, nullptr};
     int skm_part_threads_ = 128;
-    void* skm_alloc(size_t bytes);
+    // the exchange arena: [halves][nseg | ring | offsets | world x cap_pair records]; xa_peer_[o] = owner o's arena as mapped here
+    SkmArenaGeom xa_geom_;
+    DevBuf xa_buf_;
+    int xa_halves_ = 1;
+    std::vector<void*> xa_peer_, xa_ipc_opened_;
+    u64 xa_send_epoch_ = 0, xa_flushed_epoch_ = 0;
+    u32 xa_seg_idx_ = 0;
+    bool xa_dirty_ = false;
     void skm_init();
-    void skm_count_chunk(size_t ci);
-    void skm_scatter_last(u64 total);
+    void xchg_default_setup();
+    void skm_send_args(void* out_args, int half);
+    void skm_make_room(u64 n_rec, bool host_text);
+    void skm_feed_chunk(size_t ci);
+    void skm_fence();
     void skm_flush();
     void skm_reset();
     void skm_release();
 public:
-    // multi-GPU exchange surface (C-ABI: pgb200_exchange_*)
-    static constexpr int tuple_words() { return NW == 2 ? 4 : 8; }
-    void xchg_setup(uint64_t cap_tuples) override;
-    void xchg_export(int buf, void* handle64) override;
-    void xchg_import(int peer, int buf, const void* handle64) override;
-    void xchg_counts(uint64_t* counts) override;
-    void xchg_scatter(int buf, const uint64_t* base) override;
-    void xchg_apply(int buf, uint64_t n) override;
-    const void* exchange_buffer(uint64_t* ranges, int* tuple_bytes) override {
-        const int world = prm_.world > 1 ? prm_.world : 1;
-        for (int o = 0; o <= world; o++) ranges[o] = owner_start_.size() == (size_t)world + 1 ? owner_start_[o] : 0;
-        *tuple_bytes = tuple_words() * 8;
-        sync();
-        return tuple_buf().p;
-    }
-    void exchange_clear() override { owner_start_.clear(); n_tuples_ = 0; }
-    void apply_received(const void* tuples, uint64_t n) override {
-        if (!n) return;
-        ensure_table(0);
-        ensure_table(n);
-        PG_CUDA(cudaEventRecord(ev_[2], st_));
-        apply_tuples(reinterpret_cast<const u64*>(tuples), n);
-        PG_CUDA(cudaEventRecord(ev_[3], st_));
-        sync();
-        float ms;
-        PG_CUDA(cudaEventElapsedTime(&ms, ev_[2], ev_[3]));
-        p1_.ms_insert += ms;
-    }
+    void xchg_setup(uint64_t cap_records) override;
+    void xchg_export(void* handle64) override;
+    void xchg_import(int peer, const void* handle64) override;
+    void* xchg_base() override;
+    void xchg_import_ptr(int peer, int peer_device, void* base) override;
+    void xchg_fence() override { skm_fence(); }
+    void flush() override { skm_flush(); }
 
     // helpers
     void ensure_table(u64 need_free);

@@ -60,6 +60,9 @@ extern "C" pgb200_engine* pgb200_create(const pgb200_params* p) {
         q.device = p->device; q.max_rd_len = p->max_rd_len > 0 ? p->max_rd_len : 100; q.table_slots = p->table_slots;
         q.verbose = p->verbose; q.world = p->world > 0 ? p->world : 1; q.rank = p->rank;
         if (q.K < 13 || q.K % 2 == 0 || q.K > (q.flavour127 ? 127 : 63)) throw std::runtime_error("pgb200: K must be odd, 13..63 (63-mer flavour) or 13..127 (127-mer flavour)");
+        // first-occurrence rank = (read ordinal << 16) | k-mer position: positions must fit 16 bits
+        if (q.max_rd_len - q.K + 1 > 65536) throw std::runtime_error("pgb200: max_rd_len - K + 1 must not exceed 65536 (k-mer positions are 16-bit)");
+        if (q.world > 16 || q.rank < 0 || q.rank >= q.world) throw std::runtime_error("pgb200: world must be 1..16 and 0 <= rank < world");
         pgb200_engine* h = new pgb200_engine;
         h->prm = q;
         h->e = make_engine(q);
@@ -86,24 +89,20 @@ extern "C" int pgb200_feed_text(pgb200_engine* e, const char* text, size_t nbyte
     PG_TRY e->e->feed_text(text, nbytes, on_device != 0, fastq, ord_base, ord_stride, reverse_seq, maxlen); PG_CATCH
 }
 extern "C" uint64_t pgb200_last_chunk_records(pgb200_engine* e) { return e->e->last_chunk_records(); }
-extern "C" const void* pgb200_exchange_buffer(pgb200_engine* e, uint64_t* ranges, int* tuple_bytes) {
-    try { return e->e->exchange_buffer(ranges, tuple_bytes); } catch (const std::exception& ex) { g_err = ex.what(); return nullptr; }
-}
-extern "C" int pgb200_exchange_clear(pgb200_engine* e) { PG_TRY e->e->exchange_clear(); PG_CATCH }
-extern "C" int pgb200_apply_tuples(pgb200_engine* e, const void* dev_tuples, uint64_t n) { PG_TRY e->e->apply_received(dev_tuples, n); PG_CATCH }
-extern "C" int pgb200_xchg_setup(pgb200_engine* e, uint64_t cap_tuples) { PG_TRY e->e->xchg_setup(cap_tuples); PG_CATCH }
-extern "C" int pgb200_xchg_export(pgb200_engine* e, int buf, void* handle64) { PG_TRY e->e->xchg_export(buf, handle64); PG_CATCH }
-extern "C" int pgb200_xchg_import(pgb200_engine* e, int peer, int buf, const void* handle64) { PG_TRY e->e->xchg_import(peer, buf, handle64); PG_CATCH }
-extern "C" int pgb200_xchg_counts(pgb200_engine* e, uint64_t* counts) { PG_TRY e->e->xchg_counts(counts); PG_CATCH }
-extern "C" int pgb200_xchg_scatter(pgb200_engine* e, int buf, const uint64_t* base) { PG_TRY e->e->xchg_scatter(buf, base); PG_CATCH }
-extern "C" int pgb200_xchg_apply(pgb200_engine* e, int buf, uint64_t n) { PG_TRY e->e->xchg_apply(buf, n); PG_CATCH }
+extern "C" int pgb200_xchg_setup(pgb200_engine* e, uint64_t cap_records) { PG_TRY e->e->xchg_setup(cap_records); PG_CATCH }
+extern "C" int pgb200_xchg_export(pgb200_engine* e, void* handle64) { PG_TRY e->e->xchg_export(handle64); PG_CATCH }
+extern "C" int pgb200_xchg_import(pgb200_engine* e, int peer, const void* handle64) { PG_TRY e->e->xchg_import(peer, handle64); PG_CATCH }
+extern "C" void* pgb200_xchg_base(pgb200_engine* e) { try { return e->e->xchg_base(); } catch (const std::exception& ex) { g_err = ex.what(); return nullptr; } }
+extern "C" int pgb200_xchg_import_ptr(pgb200_engine* e, int peer, int peer_device, void* base) { PG_TRY e->e->xchg_import_ptr(peer, peer_device, base); PG_CATCH }
+extern "C" int pgb200_xchg_fence(pgb200_engine* e) { PG_TRY e->e->xchg_fence(); PG_CATCH }
+extern "C" int pgb200_flush(pgb200_engine* e) { PG_TRY e->e->flush(); PG_CATCH }
 extern "C" int pgb200_finish_pass1(pgb200_engine* e, pgb200_pass1_stats* st) {
     PG_TRY
     Pass1Stats s;
     e->e->finish_pass1(&s);
     if (st) {
         st->records = s.records; st->reads_kept = s.reads_kept; st->instances = s.instances; st->distinct = s.distinct;
-        st->table_slots = s.table_slots; st->launches = s.launches; st->ms_decode = s.ms_decode; st->ms_insert = s.ms_insert;
+        st->table_slots = s.table_slots; st->launches = s.launches; st->ms_decode = s.ms_decode; st->ms_insert = s.ms_insert; st->ms_apply = s.ms_apply;
     }
     PG_CATCH
 }
@@ -189,7 +188,6 @@ extern "C" int pgb200_read2edge(pgb200_engine* e, const char* prefix, pgb200_gra
     if (st) { st->deleted_reads = ps.deleted_reads; st->arcs = ps.arcs; }
     PG_CATCH
 }
-static uint64_t g_num_ed_for_basic = 0;
 extern "C" int pgb200_output_vertex(pgb200_engine* e, const char* prefix, pgb200_graph_stats* st) {
     PG_TRY
     std::string vt;
@@ -198,11 +196,11 @@ extern "C" int pgb200_output_vertex(pgb200_engine* e, const char* prefix, pgb200
     write_file(std::string(prefix) + ".vertex", vt.data(), vt.size());
     fprintf(stderr, "%llu vertex(es) output.\n", (unsigned long long)nv);
     char buf[512];
-    uint64_t num_ed = st ? st->num_ed : g_num_ed_for_basic;
+    const uint64_t num_ed = e->e->num_ed();   // the engine's own count (st is an output here)
     int n = snprintf(buf, sizeof buf, "VERTEX %llu K %d\n\nEDGEs %llu\n\nMaxReadLen %d MinReadLen %d MaxNameLen %d\n", (unsigned long long)nv,
                      e->prm.K, (unsigned long long)num_ed, e->prm.max_rd_len, 0, 256);
     write_file(std::string(prefix) + ".preGraphBasic", buf, n);
-    if (st) st->vertices = nv;
+    if (st) { st->vertices = nv; st->num_ed = num_ed; }
     PG_CATCH
 }
 
@@ -347,6 +345,9 @@ struct Feeder {
             if (have == 0) break;
             size_t cut;
             if (eof) {
+                while (have > 1 && pin[have - 1] == '\n' && pin[have - 2] == '\n') have--;   // trailing blank lines are harmless
+                if (have == 1 && pin[0] == '\n') have = 0;
+                if (have == 0) break;
                 cut = have;
             } else {
                 cut = last_record_start(pin, have, fastq);

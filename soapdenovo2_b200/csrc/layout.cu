@@ -190,8 +190,6 @@ template <int NW>
 void EngineT<NW>::build_layout() {
     const int P = prm_.P;
     if (P < 1 || P > 255) throw std::runtime_error("pgb200: -p must be in 1..255 (reference thread ids are unsigned char)");
-    sync_apply();
-    flush_batch();      // nothing may still be waiting to be inserted
     settle_timing();
     read_counters();
     n_nodes_ = h_cnt_[C_DISTINCT];

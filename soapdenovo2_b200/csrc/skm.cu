@@ -1,85 +1,149 @@
-// skm.cu -- aggregated pass 1 (default for device-resident text; PGB200_SKM=0/1 forces): super-k-mer partition per chunk, one shared-memory aggregation per bucket, ONE global
-// table update per distinct k-mer.  Replaces, for the same result, the per-instance k_chop_insert (pass1.cu), whose speed is pinned
-// to the DRAM random-access rate (profiles/r01_rmw_ubench.md).  Logic shared with the host tests lives in skm.cuh.
+// skm.cu -- aggregated pass 1 (the default insert path, and the ONLY one across GPUs): super-k-mer partition per chunk, run records
+// scattered straight into the memory of the GPU that owns their bucket, one shared-memory aggregation per bucket, ONE global table
+// update per distinct k-mer.  Logic shared with the host tests lives in skm.cuh.
 //
-//   feed_text(chunk c):   k_skm_part<false>  count runs per bucket           -> segoff_c[B+1] (k_skm_offsets), bucket_inst[B] += k-mers
-//   feed_text(chunk c+1): k_skm_part<true>   write the 8-byte run records of chunk c into its per-bucket segments (the record count
-//                                            of chunk c is read with chunk c+1's one host sync: no extra synchronisation)
-//   flush (finish_pass1 / 64 chunks pending): k_skm_apply over bucket ranges sized to the free room of the global table
+//   feed_text(chunk):  k_skm_count    minimizers of every read -> runs, run count per bucket, runs kept in a side buffer
+//                      device_scan    bucket counts -> offsets of the chunk's bucket-major record blob
+//                      k_skm_publish  reserves room for the blob in every owner's arena (sender-private region: no coordination),
+//                                     writes the segment descriptor and the owner's slice of the offsets INTO THE OWNER'S MEMORY
+//                      k_skm_scatter  builds the self-contained records and stores each one at its final position in its owner's
+//                                     arena: plain stores for the local GPU, NVLink peer stores (CUDA IPC / peer access mappings)
+//                                     for the others.  Partition and "all-to-all" are the same kernel; no library collective, no
+//                                     staging buffer, no second pass over the records.
+//   flush (end of pass 1 / arena full):  k_skm_apply over the owned buckets; buckets whose worst case does not fit the global table
+//                                     are deferred, the table grows, the deferred buckets run again.
+// Replaces, for the same result, chopKmer4read + the owner filter + put_kmerset (prlHashReads.c:163-259, 79-90; newhash.c:473-528).
 #include "engine_impl.cuh"
 #include "skm.cuh"
+#include "scan.cuh"
 
 namespace pgb {
 
 constexpr int SKM_PART_THREADS = 128;
 constexpr int SKM_APPLY_THREADS = 256;
-constexpr int SKM_LOG2_SLOTS = 11;
-constexpr int SKM_SLOTS = 1 << SKM_LOG2_SLOTS;                    // shared-memory table slots per CTA (32 B/slot at K<=63: 64 KB, 3 CTAs per SM)
+#ifndef SKM_LOG2_SLOTS
+#define SKM_LOG2_SLOTS 11
+#endif
+constexpr int SKM_SLOTS = 1 << SKM_LOG2_SLOTS;                       // shared-memory table slots per CTA (32 B/slot at K<=63: 64 KB, 3 CTAs per SM)
 constexpr int SKM_SOFT_LIMIT = SKM_SLOTS - SKM_APPLY_THREADS - 64;   // claims stop here: the table can never fill up completely
-
-struct SkmChunkDev {
-    const u64* words;
-    const u32* lens;
-    const u64* recs;
-    const u32* segoff;
-    u64 ord_base, ord_stride;
-};
-
-// ------------------------------------------------------------------------------------------------ partition
-// The counting pass also leaves the runs of every read in a side buffer (SKM_SIDE_RUNS x 4 B per read: bucket | count << 20 |
-// last << 25; start positions are the running sum of the counts), so that the scatter pass does not have to find the minimizers
-// again; reads with more runs than that are re-scanned there.
+constexpr int SKM_TILE = 64;                                         // records staged in shared memory per tile
 constexpr int SKM_SIDE_RUNS = 16;
+constexpr int SKM_MAXW = 16;                                         // GPUs of one box
+
+// ------------------------------------------------------------------------------------------------ partition: count
 struct CountEmit {
     u32* cnt;
-    u64* inst;
     u32* side;
     int nrun;
     __device__ __forceinline__ void operator()(u32 b, int, int n, bool last) {
         atomicAdd(&cnt[b], 1u);
-        atomicAdd(&inst[b], (u64)n);
-        if (nrun < SKM_SIDE_RUNS) side[nrun] = b | ((u32)n << 20) | (last ? 1u << 25 : 0u);
+        if (nrun < SKM_SIDE_RUNS) side[nrun] = skm_side_pack(b, n, last);
         nrun++;
     }
 };
-struct ScatterEmit {
-    u32* cursor;
-    const u32* segoff;
-    u64* recs;
-    u32 read_idx;
-    __device__ __forceinline__ void operator()(u32 b, int s, int n, bool last) {
-        u32 i = atomicAdd(&cursor[b], 1u);
-        recs[(u64)segoff[b] + i] = skm_pack(read_idx, s, n, last);
-    }
-};
 
-template <bool SCATTER>
-__global__ void __launch_bounds__(SKM_PART_THREADS) k_skm_part(SkmGeom g, const u64* __restrict__ words, const u32* __restrict__ lens, u64 n_rec, int W64,
-                                                              u32* cnt_or_cursor, u64* inst, const u32* __restrict__ segoff, u64* recs, u32* side, u8* nruns) {
+__global__ void __launch_bounds__(SKM_PART_THREADS) k_skm_count(SkmGeom g, const u64* __restrict__ words, const u32* __restrict__ lens, u64 n_rec, int W64,
+                                                               u32* cnt, u32* side, u8* nruns) {
     extern __shared__ u32 s_ring[];   // [2 * g.w][blockDim.x]: one column per thread, bank = thread -> conflict-free
     for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += (u64)gridDim.x * blockDim.x) {
-        const int L = (int)lens[r];
-        const u64* wp = words + r * (u64)W64;
-        if (SCATTER) {
-            // only the reads whose runs did not fit the side buffer (k_skm_scatter_side handles the rest)
-            if (nruns[r] != 255) continue;
-            ScatterEmit e{cnt_or_cursor, segoff, recs, (u32)r};
-            skm_scan_read(g, wp, L, s_ring + threadIdx.x, (int)blockDim.x, e);
-        } else {
-            CountEmit e{cnt_or_cursor, inst, side + r * SKM_SIDE_RUNS, 0};
-            skm_scan_read(g, wp, L, s_ring + threadIdx.x, (int)blockDim.x, e);
-            nruns[r] = e.nrun <= SKM_SIDE_RUNS ? (u8)e.nrun : (u8)255;
-        }
+        CountEmit e{cnt, side + r * SKM_SIDE_RUNS, 0};
+        skm_scan_read(g, words + r * (u64)W64, (int)lens[r], s_ring + threadIdx.x, (int)blockDim.x, e);
+        nruns[r] = e.nrun <= SKM_SIDE_RUNS ? (u8)e.nrun : (u8)255;
     }
 }
 
-// scatter pass for the reads whose runs are in the side buffer: no minimizer work, just cursors and 8-byte stores
-__global__ void __launch_bounds__(256) k_skm_scatter_side(const u32* __restrict__ side, const u8* __restrict__ nruns, u64 n_rec, u32* cursor,
-                                                          const u32* __restrict__ segoff, u64* recs, u32* n_overflow) {
-    unsigned ovf = 0;
+struct BucketCntIn {
+    const u32* a;
+    __device__ u64 operator()(u64 i) const { return a[i]; }
+};
+struct BucketOffOut {
+    u32* a;
+    __device__ void operator()(u64 i, u64 prefix, u64) const { a[i] = (u32)prefix; }
+};
+
+// ------------------------------------------------------------------------------------------------ partition: publish + scatter
+struct SkmSendArgs {
+    u32 n_buckets;
+    int world, rank;
+    int own_shift;            // >= 0: owner(b) = b >> own_shift (power-of-two split), else the generic range search
+    u32 seg_idx, max_seg, bo_stride;
+    u64 cap_pair;
+    const u32* segoff;        // [B] exclusive offsets of this chunk's blob (bucket-major), *total = record count
+    const u64* total;
+    u64* cursor;              // [world] records this GPU has already placed in owner o's region this epoch
+    u64* dst_delta;           // [world] out: position of record i of bucket b = dst_delta[o] + segoff[b] + i   (mod 2^64)
+    u32* dst_ok;              // [world] out: 0 = the blob does not fit owner o's region (error raised, records dropped)
+    // this epoch's half of every owner's arena, as mapped into this process
+    u32* peer_nseg[SKM_MAXW];
+    SkmSegDesc* peer_ring[SKM_MAXW];
+    u32* peer_segoff[SKM_MAXW];
+    u64* peer_recs[SKM_MAXW];   // start of THIS sender's region in owner o's arena
+    u64* counters;
+};
+__device__ __forceinline__ int skm_owner(const SkmSendArgs& a, u32 b) {
+    return a.own_shift >= 0 ? (int)(b >> a.own_shift) : skm_owner_of(a.n_buckets, a.world, b);
+}
+__device__ __forceinline__ u32 skm_segoff_at(const SkmSendArgs& a, u32 b) { return b < a.n_buckets ? a.segoff[b] : (u32)*a.total; }
+
+__global__ void __launch_bounds__(256) k_skm_publish(SkmSendArgs a) {
+    if (blockIdx.x == 0 && (int)threadIdx.x < a.world) {
+        const int o = threadIdx.x;
+        const u32 lo = skm_owner_lo(a.n_buckets, a.world, o), hi = o + 1 < a.world ? skm_owner_lo(a.n_buckets, a.world, o + 1) : a.n_buckets;
+        const u32 first = skm_segoff_at(a, lo), n = skm_segoff_at(a, hi) - first;
+        const u64 base = a.cursor[o];
+        const bool fits = base + n <= a.cap_pair;
+        if (!fits) atomicAdd(&a.counters[C_XERR], 1ull);
+        a.dst_ok[o] = fits ? 1u : 0u;
+        a.dst_delta[o] = base - (u64)first;
+        if (fits) a.cursor[o] = base + n;
+        SkmSegDesc d;
+        d.rec_off = base;
+        d.n_recs = fits ? n : 0u;
+        d.pad = 0;
+        a.peer_ring[o][(u64)a.rank * a.max_seg + a.seg_idx] = d;
+        a.peer_nseg[o][a.rank] = a.seg_idx + 1;
+    }
+    // the owner's slice of the offsets, relative to the blob: entry (b - lo) for its buckets, plus the end entry
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < (u64)a.n_buckets + a.world; i += (u64)gridDim.x * blockDim.x) {
+        int o;
+        u32 b;
+        if (i < a.n_buckets) { b = (u32)i; o = skm_owner(a, b); }
+        else { o = (int)(i - a.n_buckets); b = o + 1 < a.world ? skm_owner_lo(a.n_buckets, a.world, o + 1) : a.n_buckets; }   // end entry of owner o
+        const u32 lo = skm_owner_lo(a.n_buckets, a.world, o);
+        const u32 first = skm_segoff_at(a, lo);
+        a.peer_segoff[o][((u64)a.rank * a.max_seg + a.seg_idx) * a.bo_stride + (b - lo)] = skm_segoff_at(a, b) - first;
+    }
+}
+
+template <int NW>
+__device__ __forceinline__ void skm_store_rec(u64* dst, const SkmRec<NW>& r) {
+#pragma unroll
+    for (int p = 0; p < (NW + 2) / 2; p++) {
+        uint4 v;
+        v.x = (unsigned)r.w[2 * p]; v.y = (unsigned)(r.w[2 * p] >> 32);
+        v.z = (unsigned)r.w[2 * p + 1]; v.w = (unsigned)(r.w[2 * p + 1] >> 32);
+        reinterpret_cast<uint4*>(dst)[p] = v;
+    }
+}
+template <int NW>
+__device__ __forceinline__ void skm_emit_rec(const SkmSendArgs& a, u32* cursor_b, int K, const u64* wp, int W64, u64 ordinal, u32 b, int start, int n, bool last) {
+    const u32 i = atomicAdd(&cursor_b[b], 1u);
+    const int o = skm_owner(a, b);
+    if (!a.dst_ok[o]) return;
+    const u64 idx = a.dst_delta[o] + (u64)a.segoff[b] + i;
+    const SkmRec<NW> r = skm_make_rec<NW>(K, wp, W64, ordinal, start, n, last);
+    skm_store_rec<NW>(a.peer_recs[o] + idx * (NW + 2), r);
+}
+
+// one thread per read: the runs come from the side buffer (no minimizer work), the records go to their owners
+template <int NW>
+__global__ void __launch_bounds__(256) k_skm_scatter(SkmSendArgs a, int K, const u64* __restrict__ words, u64 n_rec, int W64, u64 ord_base, u64 ord_stride,
+                                                     const u32* __restrict__ side, const u8* __restrict__ nruns, u32* cursor_b) {
     for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += (u64)gridDim.x * blockDim.x) {
         const int nr = nruns[r];
-        if (nr == 255) { ovf++; continue; }
+        if (nr == 255 || nr == 0) continue;
+        const u64* wp = words + r * (u64)W64;
+        const u64 ordinal = ord_base + r * ord_stride;
         const uint4* row = reinterpret_cast<const uint4*>(side + r * SKM_SIDE_RUNS);
         int start = 0;
         for (int q = 0; q < nr; q += 4) {
@@ -88,49 +152,34 @@ __global__ void __launch_bounds__(256) k_skm_scatter_side(const u32* __restrict_
 #pragma unroll
             for (int x = 0; x < 4; x++) {
                 if (q + x >= nr) break;
-                const u32 b = e[x] & 0xFFFFFu;
-                const int n = (int)((e[x] >> 20) & 31);
-                const u32 i = atomicAdd(&cursor[b], 1u);
-                recs[(u64)segoff[b] + i] = skm_pack((u32)r, start, n, (e[x] >> 25) & 1);
+                const int n = skm_side_n(e[x]);
+                skm_emit_rec<NW>(a, cursor_b, K, wp, W64, ordinal, skm_side_bucket(e[x]), start, n, skm_side_last(e[x]));
                 start += n;
             }
         }
     }
-    if (ovf) atomicAdd(n_overflow, ovf);
 }
 
-// in-place exclusive scan of cnt[0..n) by ONE block; cnt[n] = total (also written to *total_out)
-__global__ void __launch_bounds__(1024) k_skm_offsets(u32* cnt, u32 n, u64* total_out) {
-    __shared__ u32 s_warp[32];
-    const u32 per = (n + blockDim.x - 1) / blockDim.x;
-    const u32 lo = threadIdx.x * per, hi = lo + per < n ? lo + per : n;
-    u32 sum = 0;
-    for (u32 i = lo; i < hi; i++) sum += cnt[i];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    u32 inc = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        u32 v = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += v;
-    }
-    if (lane == 31) s_warp[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-        u32 ws = s_warp[lane], wi = ws;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            u32 v = __shfl_up_sync(0xffffffffu, wi, d);
-            if (lane >= d) wi += v;
-        }
-        s_warp[lane] = wi - ws;
-        if (lane == 31) { cnt[n] = wi; *total_out = wi; }
-    }
-    __syncthreads();
-    u32 run = s_warp[wid] + inc - sum;
-    for (u32 i = lo; i < hi; i++) {
-        u32 c = cnt[i];
-        cnt[i] = run;
-        run += c;
+// reads with more than SKM_SIDE_RUNS runs (rare): full re-scan of just those reads
+template <int NW>
+struct RescanEmit {
+    const SkmSendArgs& a;
+    u32* cursor_b;
+    int K;
+    const u64* wp;
+    int W64;
+    u64 ordinal;
+    __device__ __forceinline__ void operator()(u32 b, int s, int n, bool last) { skm_emit_rec<NW>(a, cursor_b, K, wp, W64, ordinal, b, s, n, last); }
+};
+template <int NW>
+__global__ void __launch_bounds__(SKM_PART_THREADS) k_skm_rescan(SkmSendArgs a, SkmGeom g, const u64* __restrict__ words, const u32* __restrict__ lens, u64 n_rec,
+                                                                int W64, u64 ord_base, u64 ord_stride, const u8* __restrict__ nruns, u32* cursor_b) {
+    extern __shared__ u32 s_ring[];
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += (u64)gridDim.x * blockDim.x) {
+        if (nruns[r] != 255) continue;
+        const u64* wp = words + r * (u64)W64;
+        RescanEmit<NW> e{a, cursor_b, g.K, wp, W64, ord_base + r * ord_stride};
+        skm_scan_read(g, wp, (int)lens[r], s_ring + threadIdx.x, (int)blockDim.x, e);
     }
 }
 
@@ -149,9 +198,8 @@ struct SmemTable {
     u32* count;
     // Two phases with a warp barrier between them (the caller's __syncwarp over the lanes that have an instance): first every lane
     // finds or claims its slot (lanes differ only in the number of probes), then the lanes that found an existing key apply their
-    // instance TOGETHER.  Without the barrier the lanes that match on their first probe leave the loop and run the (long) update
-    // on their own while the others keep probing (ncu: the update code ran twice per step with 9 active lanes); a formulation of
-    // the loop alone does not help, ptxas produces the same code for all of them.
+    // instance TOGETHER (without the barrier the lanes that match on their first probe run the long update on their own while the
+    // others keep probing: the update code then executes several times per step with a few active lanes each).
     // find(): 1 = key present at idx, 2 = claimed by this lane (first instance already recorded), 3 = no room (caller spills)
     __device__ __forceinline__ int find(const Table<NW>& tab, const Kmer<NW>& k, unsigned left, unsigned right, u64 rank, u32& idx) const {
         idx = skm_slot_hash(k, SKM_LOG2_SLOTS);
@@ -221,97 +269,178 @@ __device__ __forceinline__ bool table_merge(const Table<NW>& t, const Kmer<NW>& 
     return claimed;
 }
 
-constexpr int SKM_MAX_CHUNKS = 64;
-constexpr int SKM_HALF_WARPS = SKM_APPLY_THREADS / 16;
-
-// words j-1 .. j+K of one read for the lane's k-mer (skm_instance): NW+2 consecutive words, zero past the read
-template <int NW>
-__device__ __forceinline__ void skm_load_words(const u64* __restrict__ wp, int W64, int j, u64 (&buf)[NW + 2]) {
-    const int w0 = skm_first_word<NW>(j);
-#pragma unroll
-    for (int x = 0; x < NW + 2; x++) buf[x] = w0 + x < W64 ? __ldg(wp + w0 + x) : 0ull;
+// the segments one aggregation launch reads, in device memory (built by k_skm_segs from what the senders published)
+struct SkmSegList {
+    const u64* recs[SKM_MAX_SEGS];
+    const u32* segoff[SKM_MAX_SEGS];
+    u32 n;
+    u32 pad;
+};
+struct SkmFlushArgs {
+    int world;
+    u32 max_seg, bo_stride;
+    u64 cap_pair;
+    int rec_words;
+    const u32* nseg;
+    const SkmSegDesc* ring;
+    const u32* segoff;
+    const u64* recs;
+    SkmSegList* segs;
+    u64* counters;
+};
+__global__ void __launch_bounds__(256) k_skm_segs(SkmFlushArgs a) {
+    __shared__ u32 s_base[SKM_MAXW + 1];
+    if (threadIdx.x == 0) {
+        u32 acc = 0;
+        for (int s = 0; s < a.world; s++) { s_base[s] = acc; acc += a.nseg[s] < a.max_seg ? a.nseg[s] : a.max_seg; }
+        s_base[a.world] = acc;
+        if (acc > (u32)SKM_MAX_SEGS) { atomicAdd(&a.counters[C_XERR], 1ull); acc = SKM_MAX_SEGS; }
+        a.segs->n = acc;
+    }
+    __syncthreads();
+    for (int s = 0; s < a.world; s++) {
+        const u32 n = s_base[s + 1] - s_base[s];
+        for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
+            const u32 j = s_base[s] + i;
+            if (j >= (u32)SKM_MAX_SEGS) continue;
+            const SkmSegDesc d = a.ring[(u64)s * a.max_seg + i];
+            a.segs->recs[j] = a.recs + ((u64)s * a.cap_pair + d.rec_off) * a.rec_words;
+            a.segs->segoff[j] = a.segoff + ((u64)s * a.max_seg + i) * a.bo_stride;
+        }
+    }
 }
 
-// One CTA per bucket (buckets handed out dynamically).  A half warp handles one run record per step, lane t the record's k-mer
-// t, taken directly from the packed read (skm_instance: no rolling, so the 16 lanes are independent).  Record s+2 and the read
-// words of record s+1 are loaded while record s is processed.
+struct SkmApplyArgs {
+    const SkmSegList* segs;
+    const u32* bucket_list;   // nullptr: buckets 0 .. n_list-1; else the deferred buckets of the previous launch
+    u32 n_list;
+    u32* next;                // dynamic bucket hand-out
+    u64* counters;            // C_RESERVED: keys the table is committed to hold; C_DEFER / C_MAXU: deferred buckets, their largest bound
+    u64 limit;
+    u32* deferred;
+};
+
+// One CTA per bucket (buckets handed out dynamically).  The bucket's records are staged through shared memory in tiles of SKM_TILE
+// (16-byte loads, coalesced per segment); an exclusive scan of their k-mer counts maps instance q of the tile to (record, position),
+// and every warp step takes 32 CONSECUTIVE instances, so all lanes are busy whatever the run lengths.
 template <int NW>
-__global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply(Table<NW> tab, KParams<NW> kp, const SkmChunkDev* __restrict__ chunks, int n_chunks, int W64,
-                                                                u32 b0, u32 b1, u32* next_bucket, u64* counters, int dbg) {
-    extern __shared__ __align__(16) u64 s_tab[];   // key[NW][S], pay[S], rnk[S], list[S] (u16)
-    __shared__ SkmChunkDev s_chunk[SKM_MAX_CHUNKS];
-    __shared__ u32 s_cum[SKM_MAX_CHUNKS + 1], s_off[SKM_MAX_CHUNKS];
-    __shared__ u32 s_count, s_bucket;
-    __shared__ unsigned s_new, s_spill;
-    SmemTable<NW> st{s_tab, s_tab + NW * SKM_SLOTS, s_tab + (NW + 1) * SKM_SLOTS, reinterpret_cast<unsigned short*>(s_tab + (NW + 2) * SKM_SLOTS), &s_count};
-    if (threadIdx.x < n_chunks) s_chunk[threadIdx.x] = chunks[threadIdx.x];
-    if (threadIdx.x == 0) { s_new = 0; s_spill = 0; }
-    for (int i = threadIdx.x; i < SKM_SLOTS; i += SKM_APPLY_THREADS) st.key[i] = EMPTY64;   // the flush re-empties what it merges
-    unsigned my_new = 0, my_spill = 0;
-    const int hw = threadIdx.x >> 4, t = threadIdx.x & 15;
+__global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply(Table<NW> tab, KParams<NW> kp, SkmApplyArgs a) {
+    constexpr int RW = NW + 2, PIECES = RW / 2;
+    extern __shared__ __align__(16) u64 s_dyn[];   // key[NW][S], pay[S], rnk[S], list[S] (u16), tile[SKM_TILE][RW]
+    __shared__ const u64* s_ptr[SKM_MAX_SEGS];
+    __shared__ u32 s_cum[SKM_MAX_SEGS + 1];
+    __shared__ u32 s_P[SKM_TILE + 1];
+    __shared__ u32 s_warp[SKM_APPLY_THREADS / 32];
+    __shared__ u32 s_count, s_bucket, s_defer;
+    __shared__ unsigned s_new;
+    u64* tile = s_dyn + (NW + 2) * SKM_SLOTS + SKM_SLOTS / 4;
+    SmemTable<NW> st{s_dyn, s_dyn + NW * SKM_SLOTS, s_dyn + (NW + 1) * SKM_SLOTS, reinterpret_cast<unsigned short*>(s_dyn + (NW + 2) * SKM_SLOTS), &s_count};
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < SKM_SLOTS; i += SKM_APPLY_THREADS) st.key[i] = EMPTY64;   // the flush re-empties what it merges
+    const int n_segs = (int)a.segs->n;
+    unsigned tot_new = 0, tot_spill = 0;
     for (;;) {
-        __syncthreads();   // previous bucket fully flushed (and s_chunk / the empty table visible on the first trip)
-        if (threadIdx.x == 0) {
-            s_bucket = b0 + atomicAdd(next_bucket, 1u);
+        __syncthreads();   // previous bucket fully flushed (and the empty table visible on the first trip)
+        if (tid == 0) {
+            const u32 i = atomicAdd(a.next, 1u);
+            s_bucket = i < a.n_list ? (a.bucket_list ? a.bucket_list[i] : i) : 0xFFFFFFFFu;
             s_count = 0;
+            s_new = 0;
         }
         __syncthreads();
         const u32 b = s_bucket;
-        if (b >= b1) break;
-        if (threadIdx.x < n_chunks) {
-            const u32* so = s_chunk[threadIdx.x].segoff;
-            u32 lo = so[b], hi = so[b + 1];
-            s_off[threadIdx.x] = lo;
-            s_cum[threadIdx.x + 1] = hi - lo;
+        if (b == 0xFFFFFFFFu) break;
+        // ---- the bucket's records: one range per segment
+        u32 cnt = 0;
+        if (tid < n_segs) {
+            const u32* so = a.segs->segoff[tid];
+            const u32 lo = so[b];
+            cnt = so[b + 1] - lo;
+            s_ptr[tid] = a.segs->recs[tid] + (u64)lo * RW;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            u32 acc = 0;
-            s_cum[0] = 0;
-            for (int c = 0; c < n_chunks; c++) { acc += s_cum[c + 1]; s_cum[c + 1] = acc; }
-        }
-        __syncthreads();
-        const u32 total = s_cum[n_chunks];
-        // record gq of the bucket -> (chunk, record); gq only grows, so the chunk cursor only moves forward
-        int cl = 0;
-        auto next_rec = [&](u32 gq, int& c) -> u64 {
-            while (gq >= s_cum[cl + 1]) cl++;
-            c = cl;
-            return __ldg(s_chunk[cl].recs + (u64)s_off[cl] + (gq - s_cum[cl]));
-        };
-        u32 g = (u32)hw;
-        int c_cur = 0, c_nxt = 0;
-        u64 rec = 0, rec_nxt = 0;
-        u64 buf[NW + 2], nbuf[NW + 2];
+        {
+            u32 inc = cnt;
 #pragma unroll
-        for (int x = 0; x < NW + 2; x++) { buf[x] = 0; nbuf[x] = 0; }
-        if (g < total) {
-            rec = next_rec(g, c_cur);
-            if (t < skm_count(rec)) skm_load_words<NW>(s_chunk[c_cur].words + (u64)skm_read(rec) * W64, W64, skm_start(rec) + t, buf);
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 v = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += v;
+            }
+            if (lane == 31) s_warp[wid] = inc;
+            __syncthreads();
+            u32 off = 0;
+            for (int w = 0; w < wid; w++) off += s_warp[w];
+            if (tid < n_segs) s_cum[tid] = off + inc - cnt;
+            if (tid == (n_segs > 0 ? n_segs - 1 : 0)) s_cum[n_segs] = n_segs > 0 ? off + inc : 0u;
         }
-        if (g + SKM_HALF_WARPS < total) rec_nxt = next_rec(g + SKM_HALF_WARPS, c_nxt);
-        // The two half warps run the loop in lockstep (same trip count, __syncwarp at the end): without it the lanes that leave the
-        // hash insert at different times stay split into groups of ~8 for the rest of the bucket (measured: 8.2 active threads per
-        // instruction, 4x the instructions issued).
-        for (;;) {
-            const bool act = g < total;
-            if (!__any_sync(0xffffffffu, act)) break;
-            // loads for the following steps first
-            u64 rec_nn = 0;
-            int c_nn = 0;
-            if (g + SKM_HALF_WARPS < total && t < skm_count(rec_nxt))
-                skm_load_words<NW>(s_chunk[c_nxt].words + (u64)skm_read(rec_nxt) * W64, W64, skm_start(rec_nxt) + t, nbuf);
-            if (g + 2 * SKM_HALF_WARPS < total) rec_nn = next_rec(g + 2 * SKM_HALF_WARPS, c_nn);
-            const int n = skm_count(rec);
-            const bool has = act && t < n;
-            const unsigned has_mask = __ballot_sync(0xffffffffu, has);   // all 32 lanes are together here
-            if (has) {
-                const int j = skm_start(rec) + t;
-                const SkmInst<NW> in = skm_instance<NW>(kp, buf, j, !(skm_last(rec) && t == n - 1));
-                const SkmChunkDev& ch = s_chunk[c_cur];
-                const u64 rank = ((ch.ord_base + (u64)skm_read(rec) * ch.ord_stride) << 16) | (u64)j;
-                if (dbg >= 2) { my_spill += skm_slot_hash(in.canon, SKM_LOG2_SLOTS) + in.left + in.right; }   // PGB200_SKM_DBG=2: no table work at all (timing only)
-                else {
+        __syncthreads();
+        const u32 R = s_cum[n_segs];
+        // ---- room in the global table: every k-mer instance could be a new key
+        if (tid == 0) {
+            const u64 bound = (u64)R * SKM_MAX_RUN;
+            const u64 old = atomicAdd((unsigned long long*)&a.counters[C_RESERVED], (unsigned long long)bound);
+            const bool defer = R > 0 && old + bound > a.limit;
+            if (defer) {
+                atomicAdd((unsigned long long*)&a.counters[C_RESERVED], (unsigned long long)(0ull - bound));
+                a.deferred[atomicAdd((unsigned long long*)&a.counters[C_DEFER], 1ull)] = b;
+                atomicMax((unsigned long long*)&a.counters[C_MAXU], (unsigned long long)bound);
+            }
+            s_defer = defer ? 1u : 0u;
+        }
+        __syncthreads();
+        if (s_defer || R == 0) continue;
+        unsigned my_new = 0;
+        for (u32 base = 0; base < R; base += SKM_TILE) {
+            const int nt = (int)(R - base < (u32)SKM_TILE ? R - base : (u32)SKM_TILE);
+            for (int p = tid; p < nt * PIECES; p += SKM_APPLY_THREADS) {
+                const int rec = p / PIECES, piece = p - rec * PIECES;
+                const u32 q = base + rec;
+                int lo = 0, hi = n_segs;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_cum[mid] <= q) lo = mid; else hi = mid;
+                }
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(s_ptr[lo] + (u64)(q - s_cum[lo]) * RW) + piece);
+                reinterpret_cast<uint4*>(tile + rec * RW)[piece] = v;
+            }
+            __syncthreads();
+            if (tid < SKM_TILE) {   // whole warps: SKM_TILE is a multiple of 32
+                const u32 n = tid < nt ? (u32)skm_rec_n(tile[tid * RW]) : 0u;
+                u32 inc = n;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const u32 v = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += v;
+                }
+                if (lane == 31) s_warp[wid] = inc;
+                s_P[tid] = inc - n;
+            }
+            __syncthreads();
+            if (tid < SKM_TILE && wid > 0) {
+                u32 off = 0;
+                for (int w = 0; w < wid; w++) off += s_warp[w];
+                s_P[tid] += off;
+            }
+            if (tid == 0) {
+                u32 tot = 0;
+                for (int w = 0; w < SKM_TILE / 32; w++) tot += s_warp[w];
+                s_P[SKM_TILE] = tot;
+            }
+            __syncthreads();
+            const u32 I = s_P[SKM_TILE];
+            for (u32 q0 = (u32)wid * 32u; q0 < I; q0 += SKM_APPLY_THREADS) {
+                const u32 q = q0 + lane;
+                const bool has = q < I;
+                const unsigned has_mask = __ballot_sync(0xffffffffu, has);
+                if (has) {
+                    const int rec = skm_pick_record(s_P, SKM_TILE, q);
+                    const int t = (int)(q - s_P[rec]);
+                    const u64* rp = tile + rec * RW;
+                    const u64 hdr = rp[0];
+                    u64 x[NW + 1];
+#pragma unroll
+                    for (int i = 0; i < NW + 1; i++) x[i] = rp[1 + i];
+                    const SkmInst<NW> in = skm_instance_rec<NW>(kp, hdr, x, t);
+                    const u64 rank = skm_rec_rank(hdr, t);
                     u32 slot;
                     const int state = st.find(tab, in.canon, in.left, in.right, rank, slot);
                     __syncwarp(has_mask);   // the lanes re-join before the counter update (see SmemTable)
@@ -319,228 +448,374 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply(Table<NW> tab, 
                     else if (state == 3) {
                         // bucket holds more distinct k-mers than the shared-memory table: this instance goes to HBM directly (same result)
                         my_new += table_insert(tab, in.canon, in.left, in.right, rank);
-                        my_spill++;
+                        tot_spill++;
                     }
                 }
+                __syncwarp();
             }
-            rec = rec_nxt; c_cur = c_nxt;
-            rec_nxt = rec_nn; c_nxt = c_nn;
-#pragma unroll
-            for (int x = 0; x < NW + 2; x++) buf[x] = nbuf[x];
-            g += SKM_HALF_WARPS;
-            __syncwarp();
+            __syncthreads();   // the tile and s_P are rewritten by the next trip
         }
-        __syncthreads();
-        // flush: one global update per distinct k-mer of the bucket, walking the claim list (every thread busy)
+        // ---- flush: one global update per distinct k-mer of the bucket, walking the claim list (every thread busy)
         const u32 n_claimed = s_count;
-        for (u32 i = threadIdx.x; i < n_claimed; i += SKM_APPLY_THREADS) {
+        for (u32 i = tid; i < n_claimed; i += SKM_APPLY_THREADS) {
             const u32 idx = st.list[i];
             Kmer<NW> k;
 #pragma unroll
             for (int w = 0; w < NW; w++) k.w[w] = st.key[w * SKM_SLOTS + idx];
-            if (dbg == 0) my_new += table_merge(tab, k, st.pay[idx], st.rnk[idx]);   // PGB200_SKM_DBG=1: no global merge (timing only)
+            my_new += table_merge(tab, k, st.pay[idx], st.rnk[idx]);
             st.key[idx] = EMPTY64;
         }
+        if (my_new) atomicAdd(&s_new, my_new);
+        tot_new += my_new;
+        __syncthreads();
+        if (tid == 0) {   // give back what the bound over-reserved
+            const u64 bound = (u64)R * SKM_MAX_RUN;
+            atomicAdd((unsigned long long*)&a.counters[C_RESERVED], (unsigned long long)(0ull - (bound - (u64)s_new)));
+        }
     }
-    if (my_new) atomicAdd(&s_new, my_new);
-    if (my_spill) atomicAdd(&s_spill, my_spill);
+    // per-CTA totals
+    __shared__ unsigned s_tot_new, s_tot_spill;
+    if (tid == 0) { s_tot_new = 0; s_tot_spill = 0; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        if (s_new) atomicAdd(&counters[C_DISTINCT], (u64)s_new);
-        if (s_spill) atomicAdd(&counters[C_MISC2], (u64)s_spill);
+    if (tot_new) atomicAdd(&s_tot_new, tot_new);
+    if (tot_spill) atomicAdd(&s_tot_spill, tot_spill);
+    __syncthreads();
+    if (tid == 0) {
+        if (s_tot_new) atomicAdd(&a.counters[C_DISTINCT], (u64)s_tot_new);
+        if (s_tot_spill) atomicAdd(&a.counters[C_MISC2], (u64)s_tot_spill);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
 template <int NW>
-static constexpr size_t skm_apply_smem() { return (size_t)(NW + 2) * SKM_SLOTS * sizeof(u64) + (size_t)SKM_SLOTS * sizeof(unsigned short); }
-static u64 next_pow2_u64(u64 x) { u64 p = 1; while (p < x) p <<= 1; return p; }
-
-template <int NW>
-void* EngineT<NW>::skm_alloc(size_t bytes) {
-    bytes = (bytes + 255) & ~(size_t)255;
-    while (skm_blk_ < skm_blocks_.size() && skm_used_ + bytes > skm_blocks_[skm_blk_].second) { skm_blk_++; skm_used_ = 0; }
-    if (skm_blk_ >= skm_blocks_.size()) {
-        size_t blk = std::max<size_t>(bytes, (size_t)512 << 20);
-        void* p = nullptr;
-        PG_CUDA(cudaMalloc(&p, blk));
-        skm_blocks_.push_back({p, blk});
-        skm_blk_ = skm_blocks_.size() - 1;
-        skm_used_ = 0;
-    }
-    void* r = static_cast<char*>(skm_blocks_[skm_blk_].first) + skm_used_;
-    skm_used_ += bytes;
-    return r;
+static constexpr size_t skm_apply_smem() {
+    return (size_t)(NW + 2) * SKM_SLOTS * sizeof(u64) + (size_t)SKM_SLOTS * sizeof(unsigned short) + (size_t)SKM_TILE * (NW + 2) * sizeof(u64);
 }
+static u64 next_pow2_u64(u64 x) { u64 p = 1; while (p < x) p <<= 1; return p; }
 
 template <int NW>
 void EngineT<NW>::skm_init() {
     if (skm_geom_.n_buckets) return;
-    u64 est = 0;   // expected number of distinct k-mers
+    const int world = prm_.world > 1 ? prm_.world : 1;
+    if (world > SKM_MAXW) throw std::runtime_error("pgb200: at most 16 GPUs");
+    u64 est = 0;   // expected number of distinct k-mers on THIS GPU
     if (prm_.table_slots) est = prm_.table_slots / 2;
-    else if (prm_.initG) est = (u64)((double)prm_.P * (double)ref_static_set_size(prm_.initG, prm_.P, prm_.flavour127 != 0) * 0.77);
-    u64 B = est ? next_pow2_u64((est + SKM_SLOTS / 2 - 1) / (SKM_SLOTS / 2)) : (1ull << 16);
-    if (B < 1024) B = 1024;
-    if (B > (1ull << 20)) B = 1ull << 20;
+    else if (prm_.initG) est = (u64)((double)prm_.P * (double)ref_static_set_size(prm_.initG, prm_.P, prm_.flavour127 != 0) * 0.77) / world;
+    u64 Bo = est ? next_pow2_u64((est + SKM_SLOTS / 2 - 1) / (SKM_SLOTS / 2)) : (1ull << 16);
+    if (Bo < 1024) Bo = 1024;
+    u64 B = Bo * world;
     if (const char* e = getenv("PGB200_SKM_BUCKETS")) B = strtoull(e, nullptr, 0);
-    if (B < 1) B = 1;
-    if (B > (1ull << 20)) B = 1ull << 20;   // the side buffer packs the bucket in 20 bits
+    if (B < (u64)world) B = world;
+    if (B > (1ull << SKM_MAX_BUCKET_BITS)) B = 1ull << SKM_MAX_BUCKET_BITS;   // the side buffer packs the bucket in 24 bits
     skm_geom_ = make_skm_geom(prm_.K, (u32)B);
-    skm_inst_.alloc(B * sizeof(u64));
+    skm_own_lo_ = skm_owner_lo((u32)B, world, prm_.rank);
+    skm_own_hi_ = prm_.rank + 1 < world ? skm_owner_lo((u32)B, world, prm_.rank + 1) : (u32)B;
+    skm_own_shift_ = -1;
+    if ((B & (B - 1)) == 0 && (world & (world - 1)) == 0 && B >= (u64)world) {
+        int s = 0;
+        while (((u64)world << s) < B) s++;
+        skm_own_shift_ = s;
+    }
+    skm_cnt_.alloc((B + 1) * sizeof(u32));
+    skm_segoff_.alloc((B + 1) * sizeof(u32));
     skm_cursor_.alloc((B + 1) * sizeof(u32));
-    skm_desc_.alloc(SKM_MAX_CHUNKS * sizeof(SkmChunkDev) + 256);
-    PG_CUDA(cudaMemsetAsync(skm_inst_.p, 0, B * sizeof(u64), st_));
+    skm_scan_.alloc(scan_scratch_elems(B) * sizeof(u64) + 256);
+    // device-side scratch: sender cursors [world], dst_delta [world], dst_ok [world], next-bucket counter, segment list, deferred lists
+    skm_misc_.alloc(4096 + sizeof(SkmSegList) + 2 * (size_t)(skm_own_hi_ - skm_own_lo_ + 1) * sizeof(u32));
+    PG_CUDA(cudaMemsetAsync(skm_misc_.p, 0, skm_misc_.bytes, st_));
     for (auto& e : ev_skm_) PG_CUDA(cudaEventCreate(&e));
     skm_part_threads_ = SKM_PART_THREADS;
     while ((size_t)skm_part_threads_ * 2 * skm_geom_.w * sizeof(u32) > 160 * 1024 && skm_part_threads_ > 32) skm_part_threads_ /= 2;
-    size_t ring = (size_t)skm_part_threads_ * 2 * skm_geom_.w * sizeof(u32);
+    const size_t ring = (size_t)skm_part_threads_ * 2 * skm_geom_.w * sizeof(u32);
     if (ring > 48 * 1024) {
-        PG_CUDA(cudaFuncSetAttribute(k_skm_part<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
-        PG_CUDA(cudaFuncSetAttribute(k_skm_part<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
+        PG_CUDA(cudaFuncSetAttribute(k_skm_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
+        PG_CUDA(cudaFuncSetAttribute(k_skm_rescan<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
     }
     PG_CUDA(cudaFuncSetAttribute(k_skm_apply<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skm_apply_smem<NW>()));
-    if (prm_.verbose) fprintf(stderr, "[pgb200] aggregated pass 1: %u buckets, minimizer length %d, window %d\n", skm_geom_.n_buckets, skm_geom_.m, skm_geom_.w);
+    if (prm_.verbose) fprintf(stderr, "[pgb200] aggregated pass 1: %u buckets (%u owned by GPU %d of %d), minimizer length %d, window %d\n", skm_geom_.n_buckets,
+                              skm_own_hi_ - skm_own_lo_, prm_.rank, world, skm_geom_.m, skm_geom_.w);
 }
 
-// count the runs of the chunk just decoded (inside the caller's "insert" event bracket)
+// ---- the exchange arena
 template <int NW>
-void EngineT<NW>::skm_count_chunk(size_t ci) {
+void EngineT<NW>::xchg_setup(uint64_t cap_records) {
     skm_init();
+    const int world = prm_.world > 1 ? prm_.world : 1;
+    if (xa_buf_.p) throw std::runtime_error("pgb200: exchange arena already set up");
+    u64 cap_pair = cap_records / world;
+    if (cap_pair < 4096) cap_pair = 4096;
+    u32 max_seg = SKM_MAX_SEGS / (world > 1 ? 1 : 1);
+    if (const char* e = getenv("PGB200_SKM_MAX_SEG")) max_seg = (u32)atoi(e);
+    if (max_seg < 1) max_seg = 1;
+    if (max_seg > (u32)SKM_MAX_SEGS) max_seg = SKM_MAX_SEGS;
+    xa_geom_ = make_skm_arena_geom(world, skm_geom_.n_buckets, max_seg, cap_pair, NW + 2);
+    xa_halves_ = world > 1 ? 2 : 1;
+    xa_buf_.alloc(xa_geom_.half_bytes * xa_halves_);
+    for (int h = 0; h < xa_halves_; h++)
+        PG_CUDA(cudaMemsetAsync(static_cast<char*>(xa_buf_.p) + h * xa_geom_.half_bytes, 0, xa_geom_.off_recs, st_));   // nseg, ring, offsets
+    sync();
+    xa_peer_.assign(world, nullptr);
+    xa_peer_[prm_.rank] = xa_buf_.p;
+    xa_send_epoch_ = 0;
+    xa_seg_idx_ = 0;
+    xa_flushed_epoch_ = 0;
+    if (prm_.verbose) fprintf(stderr, "[pgb200] exchange arena: %d x %.2f GB (%llu records per sender, %u segments per sender and epoch)\n", xa_halves_,
+                              xa_geom_.half_bytes / 1e9, (unsigned long long)cap_pair, max_seg);
+}
+template <int NW>
+void EngineT<NW>::xchg_export(void* handle64) {
+    if (!xa_buf_.p) throw std::runtime_error("pgb200: xchg_export before xchg_setup");
+    cudaIpcMemHandle_t h;
+    PG_CUDA(cudaIpcGetMemHandle(&h, xa_buf_.p));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+}
+template <int NW>
+void EngineT<NW>::xchg_import(int peer, const void* handle64) {
+    if (peer < 0 || peer >= (int)xa_peer_.size() || peer == prm_.rank) throw std::runtime_error("pgb200: xchg_import: bad peer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    PG_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    xa_peer_[peer] = p;
+    xa_ipc_opened_.push_back(p);
+}
+template <int NW>
+void EngineT<NW>::xchg_import_ptr(int peer, int peer_device, void* base) {
+    if (peer < 0 || peer >= (int)xa_peer_.size() || peer == prm_.rank) throw std::runtime_error("pgb200: xchg_import_ptr: bad peer");
+    PG_CUDA(cudaSetDevice(prm_.device));
+    int can = 0;
+    PG_CUDA(cudaDeviceCanAccessPeer(&can, prm_.device, peer_device));
+    if (!can) throw std::runtime_error("pgb200: GPUs cannot access each other's memory (no peer access)");
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) PG_CUDA(e);
+    cudaGetLastError();
+    xa_peer_[peer] = base;
+}
+template <int NW>
+void* EngineT<NW>::xchg_base() { return xa_buf_.p; }
+
+template <int NW>
+void EngineT<NW>::xchg_default_setup() {
+    if (xa_buf_.p) return;
+    if (prm_.world > 1) throw std::runtime_error("pgb200: multi-GPU engines need pgb200_xchg_setup + xchg_import before the first chunk");
+    create_table_if_needed();
+    size_t free_b = 0, total_b = 0;
+    PG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    u64 bytes = std::min<u64>((u64)free_b / 6, 16ull << 30);
+    if (const char* e = getenv("PGB200_SKM_ARENA_MB")) bytes = strtoull(e, nullptr, 0) << 20;
+    xchg_setup(bytes / ((NW + 2) * sizeof(u64)));
+}
+
+template <int NW>
+void EngineT<NW>::skm_send_args(void* out_args, int half) {
+    SkmSendArgs& a = *reinterpret_cast<SkmSendArgs*>(out_args);
+    const int world = xa_geom_.world;
+    a.n_buckets = skm_geom_.n_buckets;
+    a.world = world;
+    a.rank = prm_.rank;
+    a.own_shift = skm_own_shift_;
+    a.seg_idx = xa_seg_idx_;
+    a.max_seg = xa_geom_.max_seg;
+    a.bo_stride = xa_geom_.bo_max + 1;
+    a.cap_pair = xa_geom_.cap_pair;
+    a.segoff = skm_segoff_.template as<u32>();
+    u64* misc = skm_misc_.template as<u64>();
+    a.total = misc + 60;
+    a.cursor = misc;                 // [16]
+    a.dst_delta = misc + 16;         // [16]
+    a.dst_ok = reinterpret_cast<u32*>(misc + 32);   // [16]
+    for (int o = 0; o < world; o++) {
+        if (!xa_peer_[o]) throw std::runtime_error("pgb200: exchange peer not imported");
+        char* h = static_cast<char*>(xa_peer_[o]) + (u64)half * xa_geom_.half_bytes;
+        a.peer_nseg[o] = reinterpret_cast<u32*>(h + xa_geom_.off_nseg);
+        a.peer_ring[o] = reinterpret_cast<SkmSegDesc*>(h + xa_geom_.off_ring);
+        a.peer_segoff[o] = reinterpret_cast<u32*>(h + xa_geom_.off_segoff);
+        a.peer_recs[o] = reinterpret_cast<u64*>(h + xa_geom_.off_recs) + (u64)prm_.rank * xa_geom_.cap_pair * (NW + 2);
+    }
+    a.counters = d_cnt_;
+}
+
+// Room for the next chunk's records and segment (called OUTSIDE the caller's per-chunk event bracket: a flush times itself).
+// Single GPU: decided here.  Several GPUs: the caller fences + flushes all GPUs collectively; running out of room is an error.
+template <int NW>
+void EngineT<NW>::skm_make_room(u64 n_rec, bool host_text) {
+    skm_init();
+    xchg_default_setup();
+    const u64 worst = n_rec * (u64)std::max(1, prm_.max_rd_len - prm_.K + 1);   // every k-mer its own record
+    if (xa_geom_.world == 1) {
+        const u64 known = h_cnt_[C_XUSED];   // records in the arena as of the previous chunk (arrived with this chunk's host sync)
+        const int every = skm_flush_every_ >= 0 ? skm_flush_every_ : (host_text ? 4 : 0);
+        const bool full = xa_seg_idx_ >= xa_geom_.max_seg || known + worst > xa_geom_.cap_pair;
+        if ((full || (every > 0 && xa_seg_idx_ >= (u32)every)) && xa_seg_idx_ > 0) {
+            skm_fence();
+            skm_flush();
+        }
+    } else if (xa_seg_idx_ >= xa_geom_.max_seg) {
+        throw std::runtime_error("pgb200: too many chunks in one exchange epoch: call pgb200_xchg_fence + pgb200_flush (on all GPUs) more often");
+    }
+}
+
+// partition the chunk just decoded and deliver its records (inside the caller's "insert" event bracket)
+template <int NW>
+void EngineT<NW>::skm_feed_chunk(size_t ci) {
     const ReadChunk& ch = chunks_[ci];
     const u32 B = skm_geom_.n_buckets;
-    SkmPending pd;
-    pd.chunk = ci;
-    pd.segoff = reinterpret_cast<u32*>(skm_alloc((B + 1) * sizeof(u32)));
-    PG_CUDA(cudaMemsetAsync(pd.segoff, 0, (B + 1) * sizeof(u32), st_));
+    const int world = xa_geom_.world;
+    (void)world;
+    PG_CUDA(cudaMemsetAsync(skm_cnt_.p, 0, (B + 1) * sizeof(u32), st_));
+    PG_CUDA(cudaMemsetAsync(skm_cursor_.p, 0, (B + 1) * sizeof(u32), st_));
     const size_t ring = (size_t)skm_part_threads_ * 2 * skm_geom_.w * sizeof(u32);
     const unsigned blocks = (unsigned)std::min<u64>((ch.n_rec + skm_part_threads_ - 1) / skm_part_threads_, 148ull * 16);
     skm_side_.ensure(ch.n_rec * (SKM_SIDE_RUNS * sizeof(u32) + 1) + 256);
     u32* side = skm_side_.template as<u32>();
     u8* nruns = reinterpret_cast<u8*>(side + ch.n_rec * SKM_SIDE_RUNS);
-    k_skm_part<false><<<blocks, skm_part_threads_, ring, st_>>>(skm_geom_, ch.words, ch.len, ch.n_rec, W64_, pd.segoff, skm_inst_.template as<u64>(), nullptr, nullptr, side, nruns);
+    k_skm_count<<<blocks, skm_part_threads_, ring, st_>>>(skm_geom_, ch.words, ch.len, ch.n_rec, W64_, skm_cnt_.template as<u32>(), side, nruns);
     PG_CUDA(cudaGetLastError());
-    k_skm_offsets<<<1, 1024, 0, st_>>>(pd.segoff, B, d_cnt_ + C_MISC1);
+    u64* misc = skm_misc_.template as<u64>();
+    device_scan(BucketCntIn{skm_cnt_.template as<u32>()}, BucketOffOut{skm_segoff_.template as<u32>()}, (u64)B, skm_scan_.template as<u64>(), misc + 60, st_);
+    SkmSendArgs a;
+    skm_send_args(&a, (int)(xa_send_epoch_ % xa_halves_));
+    k_skm_publish<<<(unsigned)std::min<u64>(((u64)B + world + 255) / 256, 148ull * 8), 256, 0, st_>>>(a);
     PG_CUDA(cudaGetLastError());
-    skm_pending_.push_back(pd);
-    skm_unscattered_ = true;
-    p1_.launches += 2;
+    u32* cursor_b = skm_cursor_.template as<u32>();
+    k_skm_scatter<NW><<<(unsigned)std::min<u64>((ch.n_rec + 255) / 256, 148ull * 16), 256, 0, st_>>>(a, prm_.K, ch.words, ch.n_rec, W64_, ch.ord_base, ch.ord_stride, side, nruns, cursor_b);
+    PG_CUDA(cudaGetLastError());
+    k_skm_rescan<NW><<<blocks, skm_part_threads_, ring, st_>>>(a, skm_geom_, ch.words, ch.len, ch.n_rec, W64_, ch.ord_base, ch.ord_stride, nruns, cursor_b);
+    PG_CUDA(cudaGetLastError());
+    // the sender cursor travels to the host with the NEXT chunk's one sync (C_XUSED), so the room check above lags by one chunk
+    PG_CUDA(cudaMemcpyAsync(d_cnt_ + C_XUSED, misc, sizeof(u64), cudaMemcpyDeviceToDevice, st_));
+    xa_seg_idx_++;
+    xa_dirty_ = true;
+    p1_.launches += 7;
 }
 
-// write the records of the last counted chunk; `total` = its record count (read by the caller's host sync)
+// every record this GPU produced in the current epoch has reached its owner; the next chunks go to the other arena half
 template <int NW>
-void EngineT<NW>::skm_scatter_last(u64 total) {
-    if (!skm_unscattered_) return;
-    SkmPending& pd = skm_pending_.back();
-    const ReadChunk& ch = chunks_[pd.chunk];
-    const u32 B = skm_geom_.n_buckets;
-    pd.n_recs = total;
-    pd.recs = reinterpret_cast<u64*>(skm_alloc((total ? total : 1) * sizeof(u64)));
-    PG_CUDA(cudaMemsetAsync(skm_cursor_.p, 0, (B + 1) * sizeof(u32), st_));
-    const size_t ring = (size_t)skm_part_threads_ * 2 * skm_geom_.w * sizeof(u32);
-    const unsigned blocks = (unsigned)std::min<u64>((ch.n_rec + skm_part_threads_ - 1) / skm_part_threads_, 148ull * 16);
-    u32* side = skm_side_.template as<u32>();
-    u8* nruns = reinterpret_cast<u8*>(side + ch.n_rec * SKM_SIDE_RUNS);
-    u32* cursor = skm_cursor_.template as<u32>();
-    k_skm_scatter_side<<<(unsigned)std::min<u64>((ch.n_rec + 255) / 256, 148ull * 16), 256, 0, st_>>>(side, nruns, ch.n_rec, cursor, pd.segoff, pd.recs, cursor + B);
-    PG_CUDA(cudaGetLastError());
-    // reads with more than SKM_SIDE_RUNS runs (rare): full re-scan, restricted to those reads
-    k_skm_part<true><<<blocks, skm_part_threads_, ring, st_>>>(skm_geom_, ch.words, ch.len, ch.n_rec, W64_, cursor, nullptr, pd.segoff, pd.recs, side, nruns);
-    PG_CUDA(cudaGetLastError());
-    p1_.launches += 1;
-    skm_unscattered_ = false;
-    skm_pending_recs_ += total;
-    p1_.launches += 1;
+void EngineT<NW>::skm_fence() {
+    settle_timing();
+    sync();
+    read_counters();
+    check_format_counter();
+    if (h_cnt_[C_XERR])
+        throw std::runtime_error("pgb200: exchange arena overflow (records of a chunk did not fit their owner's region, or too many segments): "
+                                 "raise the arena capacity (pgb200_xchg_setup / PGB200_SKM_ARENA_MB) or flush more often");
+    if (!xa_buf_.p) return;
+    if (xa_dirty_ || prm_.world > 1) {
+        xa_send_epoch_++;
+        xa_seg_idx_ = 0;
+        h_cnt_[C_XUSED] = 0;
+        xa_dirty_ = false;
+        PG_CUDA(cudaMemsetAsync(skm_misc_.p, 0, 16 * sizeof(u64), st_));   // sender cursors
+        PG_CUDA(cudaMemsetAsync(d_cnt_ + C_XUSED, 0, sizeof(u64), st_));
+    }
 }
 
-// aggregate every pending chunk into the global table
+// aggregate the fenced epoch into the global table (several GPUs: only after every GPU has fenced -- the caller's barrier)
 template <int NW>
 void EngineT<NW>::skm_flush() {
-    if (skm_pending_.empty()) return;
-    settle_timing();
-    if (skm_unscattered_) {
-        read_counters();
-        PG_CUDA(cudaEventRecord(ev_skm_[0], st_));
-        skm_scatter_last(h_cnt_[C_MISC1]);
-    } else {
-        PG_CUDA(cudaEventRecord(ev_skm_[0], st_));
-    }
-    const u32 B = skm_geom_.n_buckets;
-    std::vector<u64> inst(B);
-    PG_CUDA(cudaMemcpyAsync(inst.data(), skm_inst_.p, B * sizeof(u64), cudaMemcpyDeviceToHost, st_));
-    std::vector<SkmChunkDev> desc;
-    for (auto& pd : skm_pending_) {
-        const ReadChunk& ch = chunks_[pd.chunk];
-        desc.push_back(SkmChunkDev{ch.words, ch.len, pd.recs, pd.segoff, ch.ord_base, ch.ord_stride});
-    }
-    if (desc.size() > (size_t)SKM_MAX_CHUNKS) throw std::runtime_error("pgb200: internal: too many pending chunks in skm_flush");
-    PG_CUDA(cudaMemcpyAsync(skm_desc_.p, desc.data(), desc.size() * sizeof(SkmChunkDev), cudaMemcpyHostToDevice, st_));
-    u32* d_next = reinterpret_cast<u32*>(static_cast<char*>(skm_desc_.p) + SKM_MAX_CHUNKS * sizeof(SkmChunkDev));
+    if (!xa_buf_.p || xa_flushed_epoch_ >= xa_send_epoch_) return;
+    if (xa_flushed_epoch_ + 1 != xa_send_epoch_) throw std::runtime_error("pgb200: internal: more than one unflushed exchange epoch");
+    const int half = (int)(xa_flushed_epoch_ % xa_halves_);
+    char* hb = static_cast<char*>(xa_buf_.p) + (u64)half * xa_geom_.half_bytes;
+    PG_CUDA(cudaEventRecord(ev_skm_[0], st_));
     create_table_if_needed();
-    PG_CUDA(cudaMemsetAsync(d_cnt_ + C_MISC2, 0, sizeof(u64), st_));   // spilled instances (bucket larger than the shared-memory table)
-    read_counters();   // also completes the two copies above
-    u32 b0 = 0;
+    read_counters();
+    u64* misc = skm_misc_.template as<u64>();
+    SkmSegList* segs = reinterpret_cast<SkmSegList*>(reinterpret_cast<char*>(misc) + 4096);
+    const u32 n_owned = skm_own_hi_ - skm_own_lo_;
+    u32* deferred[2] = {reinterpret_cast<u32*>(reinterpret_cast<char*>(segs) + sizeof(SkmSegList)), nullptr};
+    deferred[1] = deferred[0] + n_owned + 1;
+    u32* d_next = reinterpret_cast<u32*>(misc + 48);
+    SkmFlushArgs fa;
+    fa.world = xa_geom_.world; fa.max_seg = xa_geom_.max_seg; fa.bo_stride = xa_geom_.bo_max + 1; fa.cap_pair = xa_geom_.cap_pair; fa.rec_words = NW + 2;
+    fa.nseg = reinterpret_cast<const u32*>(hb + xa_geom_.off_nseg);
+    fa.ring = reinterpret_cast<const SkmSegDesc*>(hb + xa_geom_.off_ring);
+    fa.segoff = reinterpret_cast<const u32*>(hb + xa_geom_.off_segoff);
+    fa.recs = reinterpret_cast<const u64*>(hb + xa_geom_.off_recs);
+    fa.segs = segs;
+    fa.counters = d_cnt_;
+    k_skm_segs<<<1, 256, 0, st_>>>(fa);
+    PG_CUDA(cudaGetLastError());
     const size_t smem = skm_apply_smem<NW>();
-    int ranges = 0;
-    while (b0 < B) {
-        // as many buckets as the table has guaranteed room for (every instance could be a new key)
+    const u32* list = nullptr;
+    u32 n_list = n_owned;
+    int launches = 0, which = 0;
+    for (;;) {
         const u64 have = h_cnt_[C_DISTINCT];
-        double room = 0.80 * (double)cap_ - (double)have;
-        if (room < 0.25 * (double)cap_) room = 0.25 * (double)cap_;
-        u64 sum = 0;
-        u32 b1 = b0;
-        while (b1 < B && (b1 == b0 || (double)(sum + inst[b1]) <= room)) sum += inst[b1++];
-        ensure_table_bound(have, sum);
-        if (getenv("PGB200_SKM_STATS")) fprintf(stderr, "[pgb200]   range %d: buckets %u..%u, %llu instance(s), %llu distinct before\n", ranges, b0, b1, (unsigned long long)sum, (unsigned long long)have);
+        u64 zero3[3] = {have, 0, 0};   // C_RESERVED, C_DEFER, C_MAXU are consecutive
+        PG_CUDA(cudaMemcpyAsync(d_cnt_ + C_RESERVED, zero3, sizeof zero3, cudaMemcpyHostToDevice, st_));
         PG_CUDA(cudaMemsetAsync(d_next, 0, sizeof(u32), st_));
-        const unsigned blocks = (unsigned)std::min<u64>((u64)(b1 - b0), 148ull * (NW == 2 ? 3 : 2));
-        k_skm_apply<NW><<<blocks, SKM_APPLY_THREADS, smem, st_>>>(tab_, kp_, reinterpret_cast<const SkmChunkDev*>(skm_desc_.p), (int)desc.size(), W64_, b0, b1, d_next, d_cnt_, getenv("PGB200_SKM_DBG") ? atoi(getenv("PGB200_SKM_DBG")) : 0);
+        SkmApplyArgs aa;
+        aa.segs = segs; aa.bucket_list = list; aa.n_list = n_list; aa.next = d_next; aa.counters = d_cnt_;
+        aa.limit = (u64)(0.85 * (double)cap_);
+        aa.deferred = deferred[which];
+        const unsigned blocks = (unsigned)std::min<u64>((u64)n_list, 148ull * (NW == 2 ? 3 : 2));
+        if (blocks) k_skm_apply<NW><<<blocks, SKM_APPLY_THREADS, smem, st_>>>(tab_, kp_, aa);
         PG_CUDA(cudaGetLastError());
         p1_.launches += 1;
-        ranges++;
-        b0 = b1;
-        if (b0 < B) read_counters();
+        launches++;
+        read_counters();
+        if (h_cnt_[C_XERR]) throw std::runtime_error("pgb200: too many segments in one exchange epoch (flush more often)");
+        const u64 n_def = h_cnt_[C_DEFER];
+        if (!n_def) break;
+        // grow so that (at least) the largest deferred bucket fits, then run the deferred buckets again
+        u64 cap = cap_ * 2;
+        while (0.85 * (double)cap < (double)(h_cnt_[C_DISTINCT] + h_cnt_[C_MAXU])) cap <<= 1;
+        size_t free_b = 0, total_b = 0;
+        PG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        if (cap * sizeof(Slot<NW>) + (1ull << 28) > free_b)
+            throw std::runtime_error("pgb200: k-mer table cannot grow further (out of HBM); use more GPUs");
+        grow_table(cap);
+        list = deferred[which];
+        n_list = (u32)n_def;
+        which ^= 1;
     }
+    // the epoch's half is free again: senders may use it from the epoch after next
+    PG_CUDA(cudaMemsetAsync(hb + xa_geom_.off_nseg, 0, (size_t)xa_geom_.world * sizeof(u32), st_));
     PG_CUDA(cudaEventRecord(ev_skm_[1], st_));
-    PG_CUDA(cudaMemsetAsync(skm_inst_.p, 0, B * sizeof(u64), st_));
     PG_CUDA(cudaEventSynchronize(ev_skm_[1]));
     float ms;
     PG_CUDA(cudaEventElapsedTime(&ms, ev_skm_[0], ev_skm_[1]));
     p1_.ms_insert += ms;
-    if (prm_.verbose >= 2 || getenv("PGB200_SKM_STATS")) {
-        read_counters();
-        fprintf(stderr, "[pgb200] aggregated %zu chunk(s), %llu records, %u buckets in %d range(s): %.2f ms; %llu instance(s) spilled past the shared-memory tables; %llu distinct, table %llu slots\n",
-                skm_pending_.size(), (unsigned long long)skm_pending_recs_, B, ranges, ms, (unsigned long long)h_cnt_[C_MISC2], (unsigned long long)h_cnt_[C_DISTINCT], (unsigned long long)cap_);
-    }
-    skm_pending_.clear();
-    skm_pending_recs_ = 0;
-    skm_blk_ = 0;
-    skm_used_ = 0;
+    p1_.ms_apply += ms;
+    xa_flushed_epoch_++;
+    if (prm_.verbose >= 2 || getenv("PGB200_SKM_STATS"))
+        fprintf(stderr, "[pgb200] aggregated epoch %llu: %u owned bucket(s), %d launch(es), %.2f ms; %llu instance(s) spilled past the shared-memory tables; %llu distinct, table %llu slots\n",
+                (unsigned long long)xa_flushed_epoch_, n_owned, launches, ms, (unsigned long long)h_cnt_[C_MISC2], (unsigned long long)h_cnt_[C_DISTINCT], (unsigned long long)cap_);
 }
 
 template <int NW>
 void EngineT<NW>::skm_reset() {
-    skm_pending_.clear();
-    skm_pending_recs_ = 0;
-    skm_unscattered_ = false;
-    skm_blk_ = 0;
-    skm_used_ = 0;
-    if (skm_geom_.n_buckets) PG_CUDA(cudaMemsetAsync(skm_inst_.p, 0, (size_t)skm_geom_.n_buckets * sizeof(u64), st_));
+    // single GPU: nothing of the arena survives a reset; several GPUs: the epochs keep alternating (peers may already deliver)
+    if (xa_buf_.p && prm_.world <= 1) {
+        if (xa_dirty_) { skm_fence(); xa_flushed_epoch_ = xa_send_epoch_; PG_CUDA(cudaMemsetAsync(static_cast<char*>(xa_buf_.p) + xa_geom_.off_nseg, 0, sizeof(u32), st_)); }
+    }
 }
 
 template <int NW>
 void EngineT<NW>::skm_release() {
-    for (auto& b : skm_blocks_) cudaFree(b.first);
-    skm_blocks_.clear();
+    for (void* p : xa_ipc_opened_) cudaIpcCloseMemHandle(p);
+    xa_ipc_opened_.clear();
     for (auto& e : ev_skm_) if (e) cudaEventDestroy(e);
 }
 
-
-template void* EngineT<2>::skm_alloc(size_t); template void* EngineT<4>::skm_alloc(size_t);
-template void EngineT<2>::skm_init(); template void EngineT<4>::skm_init();
-template void EngineT<2>::skm_count_chunk(size_t); template void EngineT<4>::skm_count_chunk(size_t);
-template void EngineT<2>::skm_scatter_last(u64); template void EngineT<4>::skm_scatter_last(u64);
-template void EngineT<2>::skm_flush(); template void EngineT<4>::skm_flush();
-template void EngineT<2>::skm_reset(); template void EngineT<4>::skm_reset();
-template void EngineT<2>::skm_release(); template void EngineT<4>::skm_release();
+#define PGB_INST(NW)                                                         \
+    template void EngineT<NW>::skm_init();                                   \
+    template void EngineT<NW>::xchg_setup(uint64_t);                         \
+    template void EngineT<NW>::xchg_export(void*);                           \
+    template void EngineT<NW>::xchg_import(int, const void*);                \
+    template void EngineT<NW>::xchg_import_ptr(int, int, void*);             \
+    template void* EngineT<NW>::xchg_base();                                 \
+    template void EngineT<NW>::xchg_default_setup();                         \
+    template void EngineT<NW>::skm_send_args(void*, int);                    \
+    template void EngineT<NW>::skm_feed_chunk(size_t);                       \
+    template void EngineT<NW>::skm_make_room(u64, bool);                     \
+    template void EngineT<NW>::skm_fence();                                  \
+    template void EngineT<NW>::skm_flush();                                  \
+    template void EngineT<NW>::skm_reset();                                  \
+    template void EngineT<NW>::skm_release();
+PGB_INST(2)
+PGB_INST(4)
 
 }   // namespace pgb

@@ -204,21 +204,21 @@ PG_D u64 table_find(const Table<NW>& t, const Kmer<NW>& k) {
     }
 }
 
-// Apply one k-mer instance (saturating counters + first-occurrence rank) with a single 128-bit CAS loop.
+// Apply one k-mer instance: saturating counters through a 64-bit CAS loop on `payload`, first-occurrence rank through an
+// atomicMin on `aux` that is only issued when this instance is an earlier occurrence than the one on record.  EVERY writer of a
+// slot's {payload, aux} words (per-instance insert, aggregated merge, spills) uses these same two 64-bit atomics: atomics of
+// different widths on overlapping words are not guaranteed to be atomic with respect to each other.
 // Order-independent: the final {payload, rank} is a pure function of the multiset of instances.
 template <int NW>
-PG_D void slot_apply(Slot<NW>* s, unsigned left, unsigned right, u64 rank) {
-    U128* pr = reinterpret_cast<U128*>(&s->payload);
-    U128 cur = ldcg128(pr);
+PG_D void slot_apply(Slot<NW>* s, u64 cur_payload, u64 cur_rank, unsigned left, unsigned right, u64 rank) {
     for (;;) {
-        U128 nxt;
-        nxt.a = payload_apply(cur.a, left, right);
-        nxt.b = rank < cur.b ? rank : cur.b;
-        if (nxt.a == cur.a && nxt.b == cur.b) return;   // saturated and not an earlier occurrence: read-only
-        U128 old = atomicCAS(pr, cur, nxt);
-        if (old.a == cur.a && old.b == cur.b) return;
-        cur = old;
+        u64 nxt = payload_apply(cur_payload, left, right);
+        if (nxt == cur_payload) break;                       // saturated: read-only
+        u64 old = atomicCAS(&s->payload, cur_payload, nxt);
+        if (old == cur_payload) break;
+        cur_payload = old;
     }
+    if (rank < cur_rank) atomicMin(&s->aux, rank);
 }
 
 // Fused find-or-claim + apply for one k-mer instance.  Returns true if this call inserted the key.
@@ -226,7 +226,9 @@ template <int NW>
 PG_D bool table_insert(const Table<NW>& t, const Kmer<NW>& k, unsigned left, unsigned right, u64 rank) {
     bool claimed;
     u64 idx = table_find_or_claim(t, k, &claimed);
-    slot_apply(t.slots + idx, left, right, rank);
+    Slot<NW>* s = t.slots + idx;
+    U128 cur = claimed ? U128{PAYLOAD_FRESH, EMPTY64} : ldcg128(&s->payload);
+    slot_apply(s, cur.a, cur.b, left, right, rank);
     return claimed;
 }
 // K <= 63: the whole 32 B slot arrives with ONE 256-bit load per probe, so a hit needs no second read before the CAS and
@@ -249,16 +251,7 @@ PG_D bool table_insert<2>(const Table<2>& t, const Kmer<2>& k, unsigned left, un
         }
         idx = (idx + 1) & t.mask;
     }
-    // 64-bit CAS on the payload word + an atomicMin on the rank only when this instance is an earlier occurrence than the one
-    // on record (a 128-bit CAS over both words measured no faster and costs twice the L2 atomic work).
-    for (;;) {
-        u64 nxt = payload_apply(cur.a, left, right);
-        if (nxt == cur.a) break;                       // saturated: read-only
-        u64 old = atomicCAS(&s->payload, cur.a, nxt);
-        if (old == cur.a) break;
-        cur.a = old;
-    }
-    if (rank < cur.b) atomicMin(&s->aux, rank);
+    slot_apply(s, cur.a, cur.b, left, right, rank);
     return claimed;
 }
 

@@ -2,7 +2,11 @@
 // tests/test_skm_host.py.  Against a naive per-position restatement of SURVEY.md A.2/A.3 it verifies, for random reads:
 //   * the runs of skm_scan_read tile the k-mer positions of every read exactly once, in order, each run <= SKM_MAX_RUN;
 //   * every k-mer of a run has the run's bucket, and a k-mer and its reverse complement have the same bucket;
-//   * skm_instance(position) yields exactly the (canonical k-mer, left, right) instance of every position of every run;
+//   * the self-contained record of every run (skm_make_rec) carries exactly what its k-mers need: skm_instance_rec(record, t) yields
+//     the (canonical k-mer, left, right) instance and the first-occurrence rank of every position of every run, whatever garbage
+//     follows the read in its packed words;
+//   * skm_pick_record maps instance q of a tile of records to (record, position) for every q;
+//   * bucket ownership ranges tile the buckets for every world size;
 //   * aggregating per bucket in two halves and merging with payload_merge equals applying all instances in read order.
 #include "../soapdenovo2_b200/csrc/skm.cuh"
 #include <cstdio>
@@ -84,8 +88,8 @@ static int run_case(int K, int n_reads, int maxlen, u32 n_buckets, bool low_comp
         // tiling
         int next = 0;
         for (auto& ru : runs) {
-            u64 pk = skm_pack(12345u, ru.start, ru.n, ru.last);
-            if (skm_read(pk) != 12345u || skm_start(pk) != ru.start || skm_count(pk) != ru.n || skm_last(pk) != ru.last) errors++;
+            const u32 sp = skm_side_pack(ru.b, ru.n, ru.last);
+            if (skm_side_bucket(sp) != ru.b || skm_side_n(sp) != ru.n || skm_side_last(sp) != ru.last) errors++;
             if (ru.last != (ru.start + ru.n == (int)ref.size())) { errors++; if (errors < 5) printf("bad last flag read %d\n", r); }
             if (ru.start != next || ru.n < 1 || ru.n > SKM_MAX_RUN || ru.b >= n_buckets) { errors++; if (errors < 5) printf("bad run read %d start %d n %d (expected start %d)\n", r, ru.start, ru.n, next); }
             next = ru.start + ru.n;
@@ -98,19 +102,31 @@ static int run_case(int K, int n_reads, int maxlen, u32 n_buckets, bool low_comp
             u64 rk = rank_base | (u64)in.j;
             if (rk < a.rank) a.rank = rk;
         }
+        // words past the read: garbage must not matter (the record masks what it copies)
+        std::vector<u64> dirty(words);
+        for (int i = L; i < 32 * (int)dirty.size(); i++) dirty[i >> 5] |= (u64)(rnd() & 3) << (2 * (i & 31));
+        const u64 ordinal = 1000ull + (u64)r * 3ull;
+        std::vector<u32> P;   // lane packing: prefix sums of the runs' k-mer counts, padded to a power of two
         for (auto& ru : runs) {
+            const SkmRec<NW> rec = skm_make_rec<NW>(K, dirty.data(), W64, ordinal, ru.start, ru.n, ru.last);
+            const SkmRec<NW> rec2 = skm_make_rec<NW>(K, words.data(), W64 + 1, ordinal, ru.start, ru.n, ru.last);
+            for (int x = 0; x < NW + 2; x++) if (rec.w[x] != rec2.w[x]) { errors++; if (errors < 5) printf("record depends on bytes past the read (read %d run at %d)\n", r, ru.start); break; }
+            const u64 h = rec.w[0];
+            if (skm_rec_n(h) != ru.n || skm_rec_start(h) != ru.start || skm_rec_last(h) != ru.last || skm_rec_ordinal(h) != ordinal || skm_rec_has_prev(h) != (ru.start > 0)) {
+                errors++;
+                if (errors < 5) printf("header round trip failed read %d\n", r);
+            }
+            u64 x[NW + 1];
+            for (int i = 0; i < NW + 1; i++) x[i] = rec.w[1 + i];
             for (int t = 0; t < ru.n; t++) {
                 if (ru.start + t >= (int)ref.size()) break;
                 const int j = ru.start + t;
-                u64 buf[NW + 2];
-                const int w0 = skm_first_word<NW>(j);
-                for (int x = 0; x < NW + 2; x++) buf[x] = w0 + x < W64 ? words[w0 + x] : 0xDEADBEEFDEADBEEFull;   // past the read: garbage must not matter
-                SkmInst<NW> si = skm_instance<NW>(kp, buf, j, !(ru.last && t == ru.n - 1));
+                SkmInst<NW> si = skm_instance_rec<NW>(kp, h, x, t);
                 Inst<NW> a{si.canon, si.left, si.right, j};
                 const Inst<NW>& b = ref[ru.start + t];
-                if (!keq(a.k, b.k) || a.left != b.left || a.right != b.right || a.j != b.j) {
+                if (!keq(a.k, b.k) || a.left != b.left || a.right != b.right || skm_rec_rank(h, t) != ((ordinal << 16) | (u64)j)) {
                     errors++;
-                    if (errors < 5) printf("instance mismatch read %d pos %d: left %u/%u right %u/%u j %d/%d keq %d\n", r, ru.start + t, a.left, b.left, a.right, b.right, a.j, b.j, (int)keq(a.k, b.k));
+                    if (errors < 5) printf("instance mismatch read %d pos %d: left %u/%u right %u/%u keq %d\n", r, ru.start + t, a.left, b.left, a.right, b.right, (int)keq(a.k, b.k));
                 }
                 u32 bk = skm_bucket_of_kmer<NW>(g, a.k), bk2 = skm_bucket_of_kmer<NW>(g, krc_n(a.k, K));
                 if (bk != ru.b || bk2 != ru.b) { errors++; if (errors < 5) printf("bucket mismatch read %d pos %d: run %u kmer %u rc %u\n", r, ru.start + t, ru.b, bk, bk2); }
@@ -122,6 +138,18 @@ static int run_case(int K, int n_reads, int maxlen, u32 n_buckets, bool low_comp
                 n_inst++;
             }
             n_runs++;
+        }
+        if (!runs.empty() && runs.size() <= 64) {
+            P.assign(65, 0);
+            u32 acc = 0;
+            for (size_t i = 0; i < 64; i++) { P[i] = acc; if (i < runs.size()) acc += (u32)runs[i].n; }
+            P[64] = acc;
+            u32 q = 0;
+            for (size_t i = 0; i < runs.size(); i++)
+                for (int t = 0; t < runs[i].n; t++, q++) {
+                    const int rr = skm_pick_record(P.data(), 64, q);
+                    if (rr != (int)i || (int)(q - P[rr]) != t) { errors++; if (errors < 5) printf("lane packing: instance %u -> record %d (expected %zu)\n", q, rr, i); }
+                }
         }
     }
     for (int h = 0; h < 2; h++)
@@ -148,8 +176,30 @@ static int run_case(int K, int n_reads, int maxlen, u32 n_buckets, bool low_comp
     return errors;
 }
 
+static int owner_case(u32 B, int world) {
+    int errors = 0;
+    u32 prev_hi = 0;
+    for (int o = 0; o < world; o++) {
+        const u32 lo = skm_owner_lo(B, world, o), hi = o + 1 < world ? skm_owner_lo(B, world, o + 1) : B;
+        if (lo != prev_hi || hi < lo) errors++;
+        prev_hi = hi;
+        for (u32 b = lo; b < hi; b++) if (skm_owner_of(B, world, b) != o) { errors++; break; }
+    }
+    if (prev_hi != B) errors++;
+    const SkmArenaGeom a = make_skm_arena_geom(world, B, 7, 1000, 4);
+    if (a.bo_max < (B + world - 1) / world || a.off_recs % 256 || a.half_bytes < a.off_recs + (u64)world * 1000 * 32) errors++;
+    return errors;
+}
+
 int main() {
     int e = 0;
+    {
+        int oe = 0;
+        for (u32 B : {1u, 2u, 7u, 10u, 1024u, 1000u, 262144u, 3u << 16})
+            for (int w = 1; w <= 16; w++) if (B >= (u32)w) oe += owner_case(B, w);
+        printf("ownership ranges: errors=%d\n", oe);
+        e += oe;
+    }
     e += run_case<2>(13, 3000, 60, 64, false);
     e += run_case<2>(21, 3000, 100, 256, false);
     e += run_case<2>(31, 2000, 150, 1000, false);

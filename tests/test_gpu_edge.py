@@ -57,6 +57,21 @@ def test_short_and_empty_pieces():
     eng.close()
 
 
+@pytest.mark.parametrize("text,fastq", [
+    (b">a\nACGTACGTAC\nGGGTTTAAAC\n>b\nACGTACGTAC\nGGGTTTAAAC\n", False),     # multi-line FASTA whose line count is a multiple of 2
+    (b"@a\nACGT\n+\nIIII\n\n@b\nACGT\n+\nIIII\n\n\n\n", True),                # stray blank lines, line count a multiple of 4
+    (b"@a\nACGT\n-\nIIII\n", True),                                        # separator line does not start with '+'
+])
+def test_malformed_records_are_rejected(text, fastq):
+    """Header lines must start with '>' / '@' and FASTQ separators with '+': the engine must not hash header letters as bases
+    (the reference's readseqInBuf keys on '>'; multi-line FASTA is out of scope, so it has to fail loudly)."""
+    eng = api.PregraphEngine(K=13, P=2, initG=1, max_rd_len=100)
+    with pytest.raises(api.EngineError):
+        eng.feed_text(text, fastq=fastq)
+        eng.finish_pass1()
+    eng.close()
+
+
 def test_truncation_and_reverse_via_api(tmp_path):
     """maxlen truncation and reverse_seq give the same table as feeding the pre-truncated / pre-reversed reads."""
     import numpy as np

@@ -17,9 +17,10 @@ def _build():
 
 @pytest.fixture(params=["direct", "aggregated"], autouse=True)
 def _insert_mode(request, monkeypatch):
-    """Every case runs twice: per-instance inserts (k_chop_insert) and the aggregated pass 1 (super-k-mer buckets, skm.cu)."""
-    if request.param == "aggregated":
-        monkeypatch.setenv("PGB200_SKM", "1")
+    """Every case runs twice: per-instance inserts (k_chop_insert, PGB200_SKM=0) and the default aggregated pass 1 (super-k-mer
+    records, skm.cu)."""
+    if request.param == "direct":
+        monkeypatch.setenv("PGB200_SKM", "0")
     else:
         monkeypatch.delenv("PGB200_SKM", raising=False)
 
@@ -117,3 +118,33 @@ def test_cli_pass1_kmerfreq_vs_reference(tmp_path):
     util.compare(ref, gpu, ["kmerFreq"])
     line = [l for l in r.stderr.splitlines() if "node(s) allocated" in l][0]
     assert line in util.run_ref(util.REF63, cfg, ref, 63, 8, ("-a", "1"))
+
+
+@pytest.mark.parametrize("K,flav,buckets,arena_mb,every", [(63, 0, "1", "0", "0"), (63, 0, "3", "1", "2"), (127, 1, "2", "0", "0"), (127, 1, "4096", "1", "3"), (31, 0, "0", "1", "1")])
+def test_aggregated_stress_paths(tmp_path, monkeypatch, K, flav, buckets, arena_mb, every):
+    """The aggregated pass 1 under stress: 1..4 buckets (every k-mer spills past the shared-memory table and buckets are deferred
+    until the tiny global table has grown), a 1 MB arena (mid-stream flushes because the arena is full), periodic flushes, many
+    small chunks.  Same table dump as the oracle."""
+    monkeypatch.delenv("PGB200_SKM", raising=False)
+    if buckets != "0":
+        monkeypatch.setenv("PGB200_SKM_BUCKETS", buckets)
+    if arena_mb != "0":
+        monkeypatch.setenv("PGB200_SKM_ARENA_MB", arena_mb)
+    if every != "0":
+        monkeypatch.setenv("PGB200_SKM_FLUSH_EVERY", every)
+    cfg = synth.scenario_pe_fastq(str(tmp_path))
+    mod, dump = str(tmp_path / "mod"), str(tmp_path / "mod.table")
+    util.run_model(util.MODEL127 if flav else util.MODEL63, cfg, mod, K, 4, ("-1", "-T", dump, "-a", "1"))
+    eng = api.PregraphEngine(K=K, P=4, initG=1, flavour127=flav, max_rd_len=150, table_slots=2048)
+    for mate, fn in enumerate(("pe_1.fq", "pe_2.fq")):
+        lines = open(tmp_path / fn, "rb").read().split(b"\n")[:-1]
+        recs = [b"\n".join(lines[i:i + 4]) + b"\n" for i in range(0, len(lines), 4)]
+        for i in range(0, len(recs), 700):
+            eng.feed_text(b"".join(recs[i:i + 700]), fastq=True, ord_base=2 * i + mate, ord_stride=2)
+    st = eng.finish_pass1()
+    assert st.table_slots > 2048
+    hist, _, _ = eng.sweeps()
+    assert api.kmerfreq_text(hist) == open(mod + ".kmerFreq", "rb").read()
+    eng.build_layout()
+    assert eng.dump_nodes() == open(dump, "rb").read()
+    eng.close()

@@ -1,6 +1,6 @@
 """CPU: the super-k-mer partition logic of the aggregated pass 1 (soapdenovo2_b200/csrc/skm.cuh) compiled for the host and checked
 against a naive per-position restatement of the instance rules: runs tile every read, bucket assignment is
-strand-symmetric, skm_instance reproduces every (k-mer, left, right) instance, payload_merge of partial aggregates equals applying
+strand-symmetric, the self-contained run records reproduce every (k-mer, left, right, rank) instance, the lane-packing map, payload_merge of partial aggregates equals applying
 all instances in read order (including saturation).  K = 13..127, both table widths.  See tests/host_skm.cu."""
 import os
 import subprocess
@@ -16,5 +16,5 @@ def test_super_kmer_partition_and_merge_on_host(tmp_path):
     assert r.returncode == 0, r.stdout[-3000:]
     lines = r.stdout.strip().splitlines()
     assert lines[-1] == "ALL OK"
-    assert len(lines) == 10 and all("errors=0" in l for l in lines[:-1])
+    assert len(lines) == 11 and all("errors=0" in l for l in lines[:-1])
     assert any("saturated=" in l and "saturated=0" not in l for l in lines[:-1])   # the saturation case really saturates
