@@ -504,7 +504,7 @@ extern "C" int pgb200_pregraph_main(int argc, char** argv, int flavour127) {
     return 0;
 }
 
-extern "C" int call_pregraph(int argc, char** argv) {
-    const char* f = getenv("PGB200_FLAVOUR");
-    return pgb200_pregraph_main(argc, argv, f && atoi(f) == 127 ? 1 : 0);
-}
+// The library's own call_pregraph has the 63-mer semantics (what dlopen / ctypes users get).  A SOAPdenovo-127mer build links
+// pregraph_shim.c (-DPGB_FLAVOUR127=1) instead: the executable's definition takes precedence, so the flavour is fixed at link
+// time exactly as the reference fixes it with -DMER63 / -DMER127 -- no environment variable is involved.
+extern "C" int call_pregraph(int argc, char** argv) { return pgb200_pregraph_main(argc, argv, 0); }

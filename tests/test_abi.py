@@ -44,3 +44,18 @@ def test_create_without_gpu_fails_loudly():
         pytest.skip("GPU present")
     with pytest.raises(api.EngineError):
         api.PregraphEngine(K=31)
+
+
+def test_dropin_links_against_reference_objects():
+    """The reference's own objects (minus the six replaced files) + pregraph_shim.o + libpregraph_b200.so link into a complete
+    SOAPdenovo binary whose call_pregraph is the shim (flavour fixed at link time) and whose engine entry comes from the library."""
+    if not os.path.isdir(os.path.join(util.ROOT, "oracle", "_ref", "o63")):
+        pytest.skip("oracle/_ref objects absent (built where /root/reference exists)")
+    subprocess.run(["bash", os.path.join(util.ROOT, "scripts", "link_dropin.sh")], check=True, capture_output=True)
+    for fl in ("63", "127"):
+        exe = os.path.join(util.ROOT, "oracle", "_ref", f"SOAPdenovo-{fl}mer-b200")
+        syms = subprocess.run(["nm", "-D", "--defined-only", exe], capture_output=True, text=True).stdout
+        und = subprocess.run(["nm", "-D", "--undefined-only", exe], capture_output=True, text=True).stdout
+        assert "pgb200_pregraph_main" in und
+        full = subprocess.run(["nm", exe], capture_output=True, text=True).stdout
+        assert " T call_pregraph" in full and " T call_heavygraph" in full and "prlRead2HashTable" not in full
