@@ -92,6 +92,13 @@ void *pgb200_xchg_base(pgb200_engine *e);
 int pgb200_xchg_import_ptr(pgb200_engine *e, int peer, int peer_device, void *base);
 int pgb200_xchg_fence(pgb200_engine *e);
 int pgb200_flush(pgb200_engine *e);
+/* 1: a chunk of up to n_rec reads surely fits this engine's arena regions and segment ring in the current epoch; 0: fence + flush all
+ * engines first (what the multi-GPU CLI does between chunks); -1: error.                                                          */
+int pgb200_xchg_room(pgb200_engine *e, uint64_t n_rec);
+/* Same process, after pass 1 + sweeps of both: fold `other`'s table shard and packed reads into `e` (peer access).  The graph phases
+ * (layout, tips, edges, pass 2) walk across buckets and run on ONE GPU: the multi-GPU CLI (PGB200_GPUS=n) absorbs every shard
+ * into GPU 0 and continues there.                                                                                                */
+int pgb200_absorb(pgb200_engine *e, pgb200_engine *other);
 int pgb200_finish_pass1(pgb200_engine *e, pgb200_pass1_stats *st);
 int pgb200_reset_pass1(pgb200_engine *e);
 /* delow (-d) + mark linear + coverage histogram: hist[c] = number of k-mers with coverage c (the .kmerFreq lines are hist[1..255]) */

@@ -9,14 +9,17 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpregraph_b200.so")
-BIN63 = os.path.join(_HERE, "bin", "pregraph-b200-63mer")
-BIN127 = os.path.join(_HERE, "bin", "pregraph-b200-127mer")
+# PGB200_BUILD selects an alternative in-tree build directory pair lib_<name>/ bin_<name>/ (kernel tuning experiments: the same
+# sources compiled with other -D parameters, `make -C soapdenovo2_b200/csrc VARIANT=<name> EXTRA=...`); default: lib/ and bin/.
+_SFX = ("_" + os.environ["PGB200_BUILD"]) if os.environ.get("PGB200_BUILD") else ""
+LIB_PATH = os.path.join(_HERE, "lib" + _SFX, "libpregraph_b200.so")
+BIN63 = os.path.join(_HERE, "bin" + _SFX, "pregraph-b200-63mer")
+BIN127 = os.path.join(_HERE, "bin" + _SFX, "pregraph-b200-127mer")
 
 EXPORTS = [
     "pgb200_last_error", "pgb200_default_params", "pgb200_create", "pgb200_destroy", "pgb200_host_alloc", "pgb200_host_free",
     "pgb200_feed_text", "pgb200_last_chunk_records",
-    "pgb200_xchg_setup", "pgb200_xchg_export", "pgb200_xchg_import", "pgb200_xchg_base", "pgb200_xchg_import_ptr", "pgb200_xchg_fence", "pgb200_flush",
+    "pgb200_xchg_setup", "pgb200_xchg_export", "pgb200_xchg_import", "pgb200_xchg_base", "pgb200_xchg_import_ptr", "pgb200_xchg_fence", "pgb200_flush", "pgb200_xchg_room", "pgb200_absorb",
     "pgb200_finish_pass1", "pgb200_reset_pass1", "pgb200_sweeps",
     "pgb200_build_layout", "pgb200_node_count", "pgb200_dump_nodes", "pgb200_remove_tips", "pgb200_kmer2edges",
     "pgb200_read2edge", "pgb200_output_vertex", "pgb200_plan_files", "pgb200_pregraph_main", "call_pregraph",
@@ -68,6 +71,8 @@ def load():
     lib.pgb200_xchg_import_ptr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.pgb200_xchg_fence.argtypes = [C.c_void_p]
     lib.pgb200_flush.argtypes = [C.c_void_p]
+    lib.pgb200_xchg_room.argtypes = [C.c_void_p, C.c_uint64]
+    lib.pgb200_absorb.argtypes = [C.c_void_p, C.c_void_p]
     lib.pgb200_finish_pass1.argtypes = [C.c_void_p, C.POINTER(Pass1Stats)]
     lib.pgb200_reset_pass1.argtypes = [C.c_void_p]
     lib.pgb200_sweeps.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -152,6 +157,12 @@ class PregraphEngine:
 
     def flush(self):
         self._ck(self.lib.pgb200_flush(self.h))
+
+    def xchg_room(self, n_rec) -> bool:
+        return self.lib.pgb200_xchg_room(self.h, n_rec) == 1
+
+    def absorb(self, other):
+        self._ck(self.lib.pgb200_absorb(self.h, other.h))
 
     def finish_pass1(self) -> Pass1Stats:
         st = Pass1Stats()

@@ -257,27 +257,30 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     if (nbytes == 0) return;
     if (nbytes >= (1ull << 32)) throw std::runtime_error("pgb200: a text chunk must be smaller than 4 GiB (feed it in pieces)");
     PG_CUDA(cudaSetDevice(prm_.device));
+    const bool use_skm = prm_.world > 1 || skm_mode_ != 0;
+    cudaStream_t sd = use_skm ? st_dec_ : st_;   // the per-instance insert needs exact counters per chunk: one stream
     const unsigned char* d_text;
     const bool host_src = !on_device;
     if (host_src) {
-        // H2D on its own stream into the buffer the previous chunk is NOT using: the copy overlaps the previous chunk's kernels
+        // H2D on its own stream into the buffer the previous chunk is NOT using: the copy overlaps the previous chunks' kernels
         DevBuf& tb = text_bufs_[text_flip_];
         text_flip_ ^= 1;
         tb.ensure(nbytes + 16);
         PG_CUDA(cudaMemcpyAsync(tb.p, text, nbytes, cudaMemcpyHostToDevice, st_copy_));
         PG_CUDA(cudaEventRecord(ev_copy_, st_copy_));
-        PG_CUDA(cudaStreamWaitEvent(st_, ev_copy_, 0));
+        PG_CUDA(cudaStreamWaitEvent(sd, ev_copy_, 0));
         d_text = tb.template as<unsigned char>();
     }
-    settle_timing();   // previous chunk's events (waits for its kernels; the copy above is already in flight)
-    PG_CUDA(cudaEventRecord(ev_[0], st_));
+    if (ev_head_ - ev_tail_ >= (unsigned)EV_RING) settle_oldest();
+    cudaEvent_t* ev = ev_ring_[ev_head_ % EV_RING];
+    PG_CUDA(cudaEventRecord(ev[0], sd));
     if (on_device) {
         d_text = reinterpret_cast<const unsigned char*>(text);
         if ((uintptr_t)text & 15) {   // the line index reads 16-byte groups: realign with one device-to-device copy
             DevBuf& tb = text_bufs_[text_flip_];
             text_flip_ ^= 1;
             tb.ensure(nbytes + 16);
-            PG_CUDA(cudaMemcpyAsync(tb.p, text, nbytes, cudaMemcpyDeviceToDevice, st_));
+            PG_CUDA(cudaMemcpyAsync(tb.p, text, nbytes, cudaMemcpyDeviceToDevice, sd));
             d_text = tb.template as<unsigned char>();
         }
     }
@@ -290,13 +293,13 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     u64* scan_tmp = reinterpret_cast<u64*>((reinterpret_cast<uintptr_t>(tile_base + n_tiles + 8) + 255) & ~(uintptr_t)255);
     const uint4* t16 = reinterpret_cast<const uint4*>(d_text);
     const unsigned nl_blocks = (unsigned)std::min<u64>((n_tiles + 7) / 8, 148ull * 16);
-    k_nl_count<<<nl_blocks, 256, 0, st_>>>(t16, (u64)nbytes, n_tiles, tile_cnt);
+    k_nl_count<<<nl_blocks, 256, 0, sd>>>(t16, (u64)nbytes, n_tiles, tile_cnt);
     PG_CUDA(cudaGetLastError());
-    device_scan(TileCntIn{tile_cnt}, TileBaseOut{tile_base}, n_tiles, scan_tmp, d_cnt_ + C_MISC0, st_);
-    // ONE host sync per chunk: line count, last byte, and the counters as of the previous chunk
+    device_scan(TileCntIn{tile_cnt}, TileBaseOut{tile_base}, n_tiles, scan_tmp, d_cnt_ + C_MISC0, sd);
+    // ONE host sync per chunk, of the decode stream: line count, last byte, and the counters as they are
     unsigned char* h_last = reinterpret_cast<unsigned char*>(h_cnt_ + C_COUNT);
-    PG_CUDA(cudaMemcpyAsync(h_last, d_text + nbytes - 1, 1, cudaMemcpyDeviceToHost, st_));
-    read_counters();
+    PG_CUDA(cudaMemcpyAsync(h_last, d_text + nbytes - 1, 1, cudaMemcpyDeviceToHost, sd));
+    read_counters_on(sd);
     check_format_counter();
     const u64 n_lines = h_cnt_[C_MISC0];
     const u64 have_distinct = h_cnt_[C_DISTINCT];
@@ -311,14 +314,14 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     u32* seq_start = line_buf_.template as<u32>();
     u32* seq_end = seq_start + n_rec;
     u8* bad = reinterpret_cast<u8*>(seq_end + n_rec);
-    PG_CUDA(cudaMemsetAsync(bad, 0, n_rec, st_));
-    if (open_tail) PG_CUDA(cudaMemsetAsync(seq_end, 0, n_rec * sizeof(u32), st_));   // FASTQ: the open line is the quality line
-    k_line_index<<<nl_blocks, 256, 0, st_>>>(t16, (u64)nbytes, n_tiles, tile_base, lshift, n_rec, seq_start, seq_end, d_cnt_);
+    PG_CUDA(cudaMemsetAsync(bad, 0, n_rec, sd));
+    if (open_tail) PG_CUDA(cudaMemsetAsync(seq_end, 0, n_rec * sizeof(u32), sd));   // FASTQ: the open line is the quality line
+    k_line_index<<<nl_blocks, 256, 0, sd>>>(t16, (u64)nbytes, n_tiles, tile_base, lshift, n_rec, seq_start, seq_end, d_cnt_);
     PG_CUDA(cudaGetLastError());
     if (open_tail && !fastq) {
         const u32 e = (u32)nbytes;
-        PG_CUDA(cudaMemcpyAsync(seq_end + n_rec - 1, &e, sizeof e, cudaMemcpyHostToDevice, st_));
-        sync();
+        PG_CUDA(cudaMemcpyAsync(seq_end + n_rec - 1, &e, sizeof e, cudaMemcpyHostToDevice, sd));
+        PG_CUDA(cudaStreamSynchronize(sd));
     }
 
     ReadChunk ch;
@@ -331,51 +334,60 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     t_c = host_now();
     {
         const u64 total = n_rec * (u64)W64_;
-        k_decode_fast<<<(unsigned)std::min<u64>((total + 255) / 256, 148ull * 64), 256, 0, st_>>>(d_text, (u64)nbytes, seq_start, seq_end, n_rec, maxlen, W64_,
-                                                                                                  ch.words, ch.len, bad);
+        k_decode_fast<<<(unsigned)std::min<u64>((total + 255) / 256, 148ull * 64), 256, 0, sd>>>(d_text, (u64)nbytes, seq_start, seq_end, n_rec, maxlen, W64_,
+                                                                                                 ch.words, ch.len, bad);
         PG_CUDA(cudaGetLastError());
         const u64 fix_warps = (n_rec + 31) / 32;
-        k_decode_fix<<<(unsigned)std::min<u64>((fix_warps + 7) / 8, 148ull * 32), 256, 0, st_>>>(d_text, seq_start, seq_end, n_rec, maxlen, reverse_seq, prm_.K, W64_,
-                                                                                               ch.words, ch.len, bad, d_cnt_);
+        k_decode_fix<<<(unsigned)std::min<u64>((fix_warps + 7) / 8, 148ull * 32), 256, 0, sd>>>(d_text, seq_start, seq_end, n_rec, maxlen, reverse_seq, prm_.K, W64_,
+                                                                                              ch.words, ch.len, bad, d_cnt_);
         PG_CUDA(cudaGetLastError());
     }
-    PG_CUDA(cudaEventRecord(ev_[1], st_));
-    const bool use_skm = prm_.world > 1 || skm_mode_ != 0;
-    if (use_skm) skm_make_room(n_rec, host_src);   // may aggregate what the arena holds (timed by itself)
-    PG_CUDA(cudaEventRecord(ev_[2], st_));
+    PG_CUDA(cudaEventRecord(ev[1], sd));
     if (use_skm) {
+        PG_CUDA(cudaEventRecord(ev_dec_done_, sd));
+        skm_make_room(n_rec, host_src);            // may launch the aggregation of what the arena holds (timed by itself)
+        PG_CUDA(cudaStreamWaitEvent(st_, ev_dec_done_, 0));
+        PG_CUDA(cudaEventRecord(ev[2], st_));
         skm_feed_chunk(chunks_.size() - 1);
     } else {
+        PG_CUDA(cudaEventRecord(ev[2], st_));
         // per-instance inserts: table capacity for the worst case of this chunk (host-side bound; growth itself syncs when it happens)
         const int per_read = maxlen - prm_.K + 1;
         ensure_table_bound(have_distinct, per_read > 0 ? n_rec * (u64)per_read : 0);
         chop_insert_chunk(ch);
     }
-    PG_CUDA(cudaEventRecord(ev_[3], st_));
-    timing_pending_ = true;
+    PG_CUDA(cudaEventRecord(ev[3], st_));
+    ev_head_++;
     if (host_src) PG_CUDA(cudaEventSynchronize(ev_copy_));   // the caller may reuse its host buffer; the kernels keep running
     p1_.launches += 8;   // newline count, 3 scan launches, line index, 2 decode launches (+ the insert side, counted there)
     last_records_ = n_rec;
     total_records_ += n_rec;
     t_e = host_now();
     if (prm_.verbose >= 2)
-        fprintf(stderr, "[pgb200] chunk %zu: %llu rec, host ms: count %.2f alloc %.2f launch %.2f (gpu so far: decode %.2f insert %.2f)\n", chunks_.size(),
-                (unsigned long long)n_rec, t_b - t_a, t_c - t_b, t_e - t_c, p1_.ms_decode, p1_.ms_insert);
+        fprintf(stderr, "[pgb200] chunk %zu: %llu rec, host ms: count %.2f alloc %.2f launch %.2f\n", chunks_.size(), (unsigned long long)n_rec, t_b - t_a, t_c - t_b,
+                t_e - t_c);
 }
 
 template <int NW>
-void EngineT<NW>::settle_timing() {
-    if (!timing_pending_) return;
-    PG_CUDA(cudaEventSynchronize(ev_[3]));
+void EngineT<NW>::settle_oldest() {
+    if (ev_tail_ == ev_head_) return;
+    cudaEvent_t* ev = ev_ring_[ev_tail_ % EV_RING];
+    PG_CUDA(cudaEventSynchronize(ev[1]));
+    PG_CUDA(cudaEventSynchronize(ev[3]));
     float ms;
-    PG_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1])); p1_.ms_decode += ms;
-    PG_CUDA(cudaEventElapsedTime(&ms, ev_[2], ev_[3])); p1_.ms_insert += ms;
-    timing_pending_ = false;
+    PG_CUDA(cudaEventElapsedTime(&ms, ev[0], ev[1])); p1_.ms_decode += ms;
+    PG_CUDA(cudaEventElapsedTime(&ms, ev[2], ev[3])); p1_.ms_insert += ms;
+    ev_tail_++;
+}
+template <int NW>
+void EngineT<NW>::settle_timing() {
+    while (ev_tail_ != ev_head_) settle_oldest();
 }
 
 template void EngineT<2>::feed_text(const char*, size_t, bool, int, uint64_t, uint64_t, int, int);
 template void EngineT<4>::feed_text(const char*, size_t, bool, int, uint64_t, uint64_t, int, int);
 template void EngineT<2>::settle_timing(); template void EngineT<4>::settle_timing();
+template void EngineT<2>::settle_oldest(); template void EngineT<4>::settle_oldest();
 template void EngineT<2>::check_format_counter(); template void EngineT<4>::check_format_counter();
 
 }   // namespace pgb

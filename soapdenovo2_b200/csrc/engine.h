@@ -78,6 +78,10 @@ public:
     virtual void xchg_import_ptr(int peer, int peer_device, void* base) = 0;
     virtual void xchg_fence() = 0;    // every record this engine produced so far has reached its owner
     virtual void flush() = 0;         // aggregate the fenced records into the table (after every engine has fenced)
+    virtual bool xchg_room(uint64_t n_rec) = 0;   // true: a chunk of n_rec reads surely fits this epoch (else: fence + flush all engines)
+    // Fold another engine of the same job into this one (its table shard and its read store; peer access required): afterwards this
+    // engine alone holds everything the graph phases need.  `other` must have finished pass 1 and its sweeps.
+    virtual void absorb(IEngine* other) = 0;
     virtual void finish_pass1(Pass1Stats* st) = 0;
     virtual void reset_pass1() = 0;   // drop reads + table (bench: repeat the step)
     virtual void sweeps(SweepStats* st) = 0;            // delow + mark linear + kmerFreq histogram

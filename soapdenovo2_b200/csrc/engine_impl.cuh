@@ -53,8 +53,9 @@ struct ReadChunk {
 };
 
 // C_RESERVED, C_DEFER, C_MAXU must stay consecutive (skm_flush resets them with one copy)
+// C_XERR .. C_MAXU must stay consecutive (an aggregation launch reports them with one copy); C_RESERVED, C_DEFER, C_MAXU are reset together
 enum Counter { C_DISTINCT = 0, C_INSTANCES, C_KEPT, C_LINEAR, C_REMOVED, C_MISC0, C_MISC1, C_MISC2, C_BADFMT, C_XERR, C_XUSED, C_RESERVED, C_DEFER, C_MAXU,
-               C_COUNT = 16 };
+               C_XSEGS, C_XEPOCH, C_COUNT = 16 };
 
 template <int NW>
 class EngineT : public IEngine {
@@ -80,8 +81,13 @@ public:
     // ---- state
     PgParams prm_;
     KParams<NW> kp_;
-    cudaStream_t st_ = nullptr;
-    cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+    // Three streams make pass 1 a pipeline: st_copy_ (H2D of chunk c+1) | st_dec_ (line index + decode of chunk c: all a chunk's host
+    // sync waits for) | st_ (partition, aggregation, every later phase).  With the per-instance insert (PGB200_SKM=0) decode runs on st_.
+    cudaStream_t st_ = nullptr, st_dec_ = nullptr;
+    static constexpr int EV_RING = 32;          // per-chunk event quads {decode begin, decode end, insert begin, insert end}
+    cudaEvent_t ev_ring_[EV_RING][4] = {};
+    cudaEvent_t ev_dec_done_ = nullptr;
+    unsigned ev_head_ = 0, ev_tail_ = 0;        // chunks [ev_tail_, ev_head_) have unsettled timings
     int W64_ = 0;   // packed words per read
     std::vector<ReadChunk> chunks_;
     uint64_t last_records_ = 0, total_records_ = 0;
@@ -98,8 +104,8 @@ public:
     int text_flip_ = 0;
     cudaStream_t st_copy_ = nullptr;   // H2D of chunk i+1 overlaps the insert of chunk i
     cudaEvent_t ev_copy_ = nullptr;
-    bool timing_pending_ = false;
-    void settle_timing();
+    void settle_timing();                        // waits for every fed chunk's kernels and books their times
+    void settle_oldest();
 
     // layout: reference geometry
     u64 set_size_ = 0;          // prime size of every reference set (static -a mode)
@@ -131,6 +137,15 @@ public:
     std::vector<void*> xa_peer_, xa_ipc_opened_;
     u64 xa_send_epoch_ = 0, xa_flushed_epoch_ = 0;
     u32 xa_seg_idx_ = 0;
+    bool xa_flush_inflight_ = false;   // an aggregation launch whose outcome (deferred buckets, time) has not been read yet
+    u64* h_flush_ = nullptr;           // pinned: {C_RESERVED, C_DEFER, C_MAXU, C_XERR} as of the end of that launch
+    cudaEvent_t ev_flush_ = nullptr;
+    void skm_close_epoch(bool hard);
+    void skm_flush_complete();
+    void skm_launch_apply(const u32* list, u32 n_list, u32* deferred_out);
+    std::vector<u64> xa_reads_cum_;   // reads fed in this epoch after 0, 1, 2, ... chunks (the fill known to the host lags behind)
+    int xa_flush_half_ = 0;
+    u64 skm_room_estimate(u64 n_rec);
     bool xa_dirty_ = false;
     void skm_init();
     void xchg_default_setup();
@@ -149,6 +164,8 @@ public:
     void xchg_import_ptr(int peer, int peer_device, void* base) override;
     void xchg_fence() override { skm_fence(); }
     void flush() override { skm_flush(); }
+    bool xchg_room(uint64_t n_rec) override;
+    void absorb(IEngine* other) override;
 
     // helpers
     void ensure_table(u64 need_free);
@@ -159,10 +176,18 @@ public:
     void* arena_alloc(size_t bytes);
     void grow_table(u64 new_cap);
     void alloc_table(u64 cap);
-    void sync() { PG_CUDA(cudaStreamSynchronize(st_)); }
-    void read_counters() {
+    void sync() {
+        if (st_dec_) PG_CUDA(cudaStreamSynchronize(st_dec_));
+        PG_CUDA(cudaStreamSynchronize(st_));
+    }
+    void read_counters() {   // everything queued so far has completed when this returns
+        if (st_dec_) PG_CUDA(cudaStreamSynchronize(st_dec_));
         PG_CUDA(cudaMemcpyAsync(h_cnt_, d_cnt_, C_COUNT * sizeof(u64), cudaMemcpyDeviceToHost, st_));
-        sync();
+        PG_CUDA(cudaStreamSynchronize(st_));
+    }
+    void read_counters_on(cudaStream_t s) {   // per-chunk sync of the decode stream only: counters of st_ work may lag
+        PG_CUDA(cudaMemcpyAsync(h_cnt_, d_cnt_, C_COUNT * sizeof(u64), cudaMemcpyDeviceToHost, s));
+        PG_CUDA(cudaStreamSynchronize(s));
     }
 };
 

@@ -33,7 +33,8 @@ struct pgb200_engine {
     PgParams prm;
 };
 
-#define PG_TRY try {
+// every engine entry point binds the calling thread to its engine's GPU first (one process may drive several engines)
+#define PG_TRY try { cudaSetDevice(e->prm.device);
 #define PG_CATCH                                   \
     }                                              \
     catch (const std::exception& ex) {             \
@@ -96,6 +97,8 @@ extern "C" void* pgb200_xchg_base(pgb200_engine* e) { try { return e->e->xchg_ba
 extern "C" int pgb200_xchg_import_ptr(pgb200_engine* e, int peer, int peer_device, void* base) { PG_TRY e->e->xchg_import_ptr(peer, peer_device, base); PG_CATCH }
 extern "C" int pgb200_xchg_fence(pgb200_engine* e) { PG_TRY e->e->xchg_fence(); PG_CATCH }
 extern "C" int pgb200_flush(pgb200_engine* e) { PG_TRY e->e->flush(); PG_CATCH }
+extern "C" int pgb200_xchg_room(pgb200_engine* e, uint64_t n_rec) { try { return e->e->xchg_room(n_rec) ? 1 : 0; } catch (const std::exception& ex) { g_err = ex.what(); return -1; } }
+extern "C" int pgb200_absorb(pgb200_engine* e, pgb200_engine* other) { PG_TRY e->e->absorb(other->e); PG_CATCH }
 extern "C" int pgb200_finish_pass1(pgb200_engine* e, pgb200_pass1_stats* st) {
     PG_TRY
     Pass1Stats s;
@@ -319,11 +322,20 @@ static size_t last_record_start(const char* buf, size_t n, bool fastq) {
     }
 }
 
+// One pinned staging buffer; chunk i goes to engine i % G.  pgb200_feed_text returns when the chunk's H2D copy is done, its kernels
+// keep running, so with several GPUs the copy of chunk i+1 (to the next GPU) overlaps the kernels of chunk i.
 struct Feeder {
-    pgb200_engine* eng;
+    std::vector<pgb200_engine*> engs;
+    size_t next = 0;          // engine of the next chunk
     char* pin = nullptr;
     size_t cap = 0;
     ~Feeder() { if (pin) pgb200_host_free(pin); }
+    void collective_flush() {
+        for (auto* e : engs) if (pgb200_xchg_fence(e)) { fprintf(stderr, "pgb200: %s\n", pgb200_last_error()); exit(-1); }
+        for (auto* e : engs) if (pgb200_flush(e)) { fprintf(stderr, "pgb200: %s\n", pgb200_last_error()); exit(-1); }
+        fed_in_epoch = 0;
+    }
+    size_t fed_in_epoch = 0;
     // streams one file; returns number of records
     uint64_t run(const std::string& fn, bool fastq, uint64_t ord_base, uint64_t ord_stride, int reverse, int maxlen) {
         fprintf(stderr, "Import reads from file:\n %s\n", fn.c_str());
@@ -356,11 +368,19 @@ struct Feeder {
                     continue;
                 }
             }
+            pgb200_engine* eng = engs[next];
+            if (engs.size() > 1) {
+                // several GPUs: room for this chunk's records in every arena region, and for its segment (128 per epoch over all GPUs)
+                const uint64_t upper = cut / (fastq ? 4 : 2) + 1;   // records <= lines / lines-per-record <= bytes / ...
+                if (fed_in_epoch + engs.size() > 120 || pgb200_xchg_room(eng, upper) != 1) collective_flush();
+            }
             if (pgb200_feed_text(eng, pin, cut, 0, fastq, ord_base + recs * ord_stride, ord_stride, reverse, maxlen)) {
                 fprintf(stderr, "readseqInLib return error! please make sure input file is correct fastq/fasta file \n(%s)\n", pgb200_last_error());
                 exit(-1);
             }
             recs += pgb200_last_chunk_records(eng);
+            next = (next + 1) % engs.size();
+            fed_in_epoch++;
             memmove(pin, pin + cut, have - cut);
             have -= cut;
         }
@@ -425,14 +445,41 @@ extern "C" int pgb200_pregraph_main(int argc, char** argv, int flavour127) {
     if (!max_rd_len) max_rd_len = 100;   // prlHashReads.c:326-329
     prm.max_rd_len = max_rd_len;
     fprintf(stderr, "In %s, %d lib(s), maximum read length %d, maximum name length %d.\n\n", cfg.c_str(), (int)libs.size(), max_rd_len, 256);
-    pgb200_engine* eng = pgb200_create(&prm);
-    if (!eng) { fprintf(stderr, "pgb200: %s\n", pgb200_last_error()); exit(-1); }
+    // ---- engines: one per GPU (PGB200_GPUS=n | all; default 1).  Pass 1 is sharded: GPU g owns bucket range g, every GPU decodes
+    // and partitions the chunks dealt to it and stores the records straight into their owners' arenas (peer access).
+    int n_gpus = 1;
+    if (const char* v = getenv("PGB200_GPUS")) {
+        int have = 0;
+        cudaGetDeviceCount(&have);
+        n_gpus = strcmp(v, "all") == 0 ? have : atoi(v);
+        if (n_gpus < 1) n_gpus = 1;
+        if (n_gpus > 16) n_gpus = 16;
+        if (prm.device + n_gpus > have) { fprintf(stderr, "pgb200: PGB200_GPUS=%d but only %d GPU(s) visible\n", n_gpus, have); exit(-1); }
+    }
     auto die = [&](const char* what) { fprintf(stderr, "pgb200: %s failed: %s\n", what, pgb200_last_error()); exit(-1); };
+    std::vector<pgb200_engine*> engs;
+    for (int g = 0; g < n_gpus; g++) {
+        pgb200_params q = prm;
+        q.device = prm.device + g;
+        q.world = n_gpus;
+        q.rank = g;
+        pgb200_engine* e = pgb200_create(&q);
+        if (!e) { fprintf(stderr, "pgb200: %s\n", pgb200_last_error()); exit(-1); }
+        engs.push_back(e);
+    }
+    pgb200_engine* eng = engs[0];
+    if (n_gpus > 1) {
+        for (auto* e : engs) if (pgb200_xchg_setup(e, 0)) die("exchange arena");
+        for (int g = 0; g < n_gpus; g++)
+            for (int h = 0; h < n_gpus; h++)
+                if (h != g && pgb200_xchg_import_ptr(engs[g], h, prm.device + h, pgb200_xchg_base(engs[h]))) die("peer access");
+        fprintf(stderr, "[pgb200] pass 1 sharded over %d GPUs (minimizer-bucket ranges, records stored peer to peer)\n", n_gpus);
+    }
     fprintf(stderr, "%d thread(s) initialized.\n", prm.P);
     uint64_t ord_next = 0, n_reads = 0;
     {
         Feeder fd;
-        fd.eng = eng;
+        fd.engs = engs;
         std::vector<PlanEntry> plan = build_plan(libs, max_rd_len);
         for (size_t i = 0; i < plan.size(); i++) {
             const PlanEntry& e = plan[i];
@@ -448,19 +495,41 @@ extern "C" int pgb200_pregraph_main(int argc, char** argv, int flavour127) {
                 ord_next += n; n_reads += n;
             }
         }
+        if (n_gpus > 1) fd.collective_flush();
     }
     pgb200_pass1_stats p1;
-    if (pgb200_finish_pass1(eng, &p1)) die("pass 1");
+    memset(&p1, 0, sizeof p1);
+    for (auto* e : engs) {
+        pgb200_pass1_stats q;
+        if (pgb200_finish_pass1(e, &q)) die("pass 1");
+        p1.distinct += q.distinct; p1.instances += q.instances; p1.table_slots += q.table_slots;
+        p1.ms_decode = std::max(p1.ms_decode, q.ms_decode); p1.ms_insert = std::max(p1.ms_insert, q.ms_insert);
+    }
     double t1 = now_s();
     fprintf(stderr, "Time spent on hashing reads: %ds, %lld read(s) processed.\n", (int)(t1 - t0), (long long)n_reads);
     fprintf(stderr, "%lli node(s) allocated, %lli kmer(s) in reads, %lli kmer(s) processed.\n", (long long)p1.distinct, (long long)p1.instances, (long long)p1.instances);
-    fprintf(stderr, "[pgb200] pass 1: %.3f s wall, decode %.1f ms + insert %.1f ms on the GPU, table %llu slots\n", t1 - t0, p1.ms_decode, p1.ms_insert, (unsigned long long)p1.table_slots);
+    fprintf(stderr, "[pgb200] pass 1: %.3f s wall, decode %.1f ms + insert %.1f ms on the GPU%s, table %llu slots\n", t1 - t0, p1.ms_decode, p1.ms_insert,
+            n_gpus > 1 ? " (slowest GPU)" : "", (unsigned long long)p1.table_slots);
     fprintf(stderr, "done hashing nodes\n");
     long long hist[256];
+    memset(hist, 0, sizeof hist);
     uint64_t lin = 0, rem = 0;
-    if (pgb200_sweeps(eng, hist, &lin, &rem)) die("sweeps");
+    for (auto* e : engs) {
+        long long h1[256];
+        uint64_t l1 = 0, r1 = 0;
+        if (pgb200_sweeps(e, h1, &l1, &r1)) die("sweeps");
+        for (int i = 0; i < 256; i++) hist[i] += h1[i];
+        lin += l1; rem += r1;
+    }
     if ((signed char)prm.D) fprintf(stderr, "%llu kmer(s) removed.\n", (unsigned long long)rem);
     fprintf(stderr, "%llu linear node(s) marked.\n", (unsigned long long)lin);
+    // The graph phases walk across buckets: the shards (tables with their swept flags, packed reads) are folded into GPU 0, which
+    // runs layout, tips, edges and pass 2 exactly as in the single-GPU case.
+    for (int g = 1; g < n_gpus; g++) {
+        if (pgb200_absorb(eng, engs[g])) die("gathering the table shards");
+        pgb200_destroy(engs[g]);
+        engs[g] = nullptr;
+    }
     {
         std::string s;
         char b[32];

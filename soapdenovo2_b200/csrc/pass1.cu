@@ -141,7 +141,7 @@ void EngineT<NW>::create_table_if_needed() {
         if (prm_.initG) {
             // the reference's own budget: P sets of the static prime size (prlHashReads.c:369-390)
             want = (u64)prm_.P * ref_static_set_size(prm_.initG, prm_.P, prm_.flavour127 != 0);
-            want = want + want / 4;
+            want = (want + want / 4) / (u64)(prm_.world > 1 ? prm_.world : 1);
         } else {
             want = 1ull << 24;
         }
@@ -191,13 +191,17 @@ void* EngineT<NW>::arena_alloc(size_t bytes) {
 template <int NW>
 void EngineT<NW>::finish_pass1(Pass1Stats* st) {
     if (prm_.world > 1) {
+        sync();
+        skm_flush_complete();
         if (xa_dirty_ || xa_flushed_epoch_ != xa_send_epoch_)
             throw std::runtime_error("pgb200: multi-GPU pass 1: call pgb200_xchg_fence, a barrier over all GPUs, then pgb200_flush before pgb200_finish_pass1");
     } else if (xa_buf_.p) {
-        skm_fence();
+        skm_close_epoch(false);
         skm_flush();
     }
     settle_timing();
+    sync();
+    skm_flush_complete();
     read_counters();
     check_format_counter();
     p1_.records = total_records_;
@@ -207,6 +211,51 @@ void EngineT<NW>::finish_pass1(Pass1Stats* st) {
     p1_.table_slots = cap_;
     n_nodes_ = p1_.distinct;
     if (st) *st = p1_;
+}
+
+// Fold another engine of the same job into this one: its table shard (disjoint keys: a k-mer lives on the GPU that owns its bucket)
+// is read over NVLink and re-inserted here with its payload and rank words, its packed reads are copied into this engine's store.
+template <int NW>
+void EngineT<NW>::absorb(IEngine* other_i) {
+    EngineT<NW>* o = dynamic_cast<EngineT<NW>*>(other_i);
+    if (!o || o == this) throw std::runtime_error("pgb200: absorb: engines of different key width");
+    PG_CUDA(cudaSetDevice(o->prm_.device));
+    o->settle_timing();
+    o->read_counters();
+    PG_CUDA(cudaSetDevice(prm_.device));
+    int can = 0;
+    PG_CUDA(cudaDeviceCanAccessPeer(&can, prm_.device, o->prm_.device));
+    if (!can) throw std::runtime_error("pgb200: GPUs cannot access each other's memory (no peer access)");
+    cudaError_t pe = cudaDeviceEnablePeerAccess(o->prm_.device, 0);
+    if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) PG_CUDA(pe);
+    cudaGetLastError();
+    settle_timing();
+    read_counters();
+    const u64 have = h_cnt_[C_DISTINCT], inc = o->h_cnt_[C_DISTINCT];
+    ensure_table_bound(have, inc);
+    if (o->tab_.slots && inc) {
+        k_rehash<NW><<<148 * 8, 256, 0, st_>>>(o->tab_, tab_);
+        PG_CUDA(cudaGetLastError());
+    }
+    const u64 sums[3] = {have + inc, h_cnt_[C_INSTANCES] + o->h_cnt_[C_INSTANCES], h_cnt_[C_KEPT] + o->h_cnt_[C_KEPT]};   // C_DISTINCT, C_INSTANCES, C_KEPT
+    PG_CUDA(cudaMemcpyAsync(d_cnt_ + C_DISTINCT, sums, sizeof sums, cudaMemcpyHostToDevice, st_));
+    for (const ReadChunk& c : o->chunks_) {
+        ReadChunk n = c;
+        const size_t wb = c.n_rec * (u64)W64_ * sizeof(u64), lb = c.n_rec * sizeof(u32);
+        n.words = reinterpret_cast<u64*>(arena_alloc(wb));
+        n.len = reinterpret_cast<u32*>(arena_alloc(lb));
+        PG_CUDA(cudaMemcpyPeerAsync(n.words, prm_.device, c.words, o->prm_.device, wb, st_));
+        PG_CUDA(cudaMemcpyPeerAsync(n.len, prm_.device, c.len, o->prm_.device, lb, st_));
+        chunks_.push_back(n);
+    }
+    sync();
+    total_records_ += o->total_records_;
+    p1_.ms_decode += o->p1_.ms_decode;
+    p1_.ms_insert += o->p1_.ms_insert;
+    p1_.ms_apply += o->p1_.ms_apply;
+    p1_.launches += o->p1_.launches;
+    n_nodes_ = have + inc;
+    h_cnt_[C_DISTINCT] = sums[0]; h_cnt_[C_INSTANCES] = sums[1]; h_cnt_[C_KEPT] = sums[2];
 }
 
 template <int NW>
@@ -296,8 +345,12 @@ EngineT<NW>::EngineT(const PgParams& p) : prm_(p) {
     kp_ = make_kparams<NW>(p.K);
     PG_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     PG_CUDA(cudaStreamCreateWithFlags(&st_copy_, cudaStreamNonBlocking));
+    PG_CUDA(cudaStreamCreateWithFlags(&st_dec_, cudaStreamNonBlocking));
+    PG_CUDA(cudaEventCreateWithFlags(&ev_dec_done_, cudaEventDisableTiming));
+    PG_CUDA(cudaEventCreate(&ev_flush_));
+    PG_CUDA(cudaHostAlloc(&h_flush_, 8 * sizeof(u64), cudaHostAllocDefault));
+    for (auto& q : ev_ring_) for (auto& e : q) PG_CUDA(cudaEventCreate(&e));
     PG_CUDA(cudaEventCreateWithFlags(&ev_copy_, cudaEventDisableTiming));
-    for (auto& e : ev_) PG_CUDA(cudaEventCreate(&e));
     PG_CUDA(cudaMalloc(&d_cnt_, C_COUNT * sizeof(u64)));
     PG_CUDA(cudaMemsetAsync(d_cnt_, 0, C_COUNT * sizeof(u64), st_));
     PG_CUDA(cudaHostAlloc(&h_cnt_, (C_COUNT + 2) * sizeof(u64), cudaHostAllocDefault));
@@ -314,7 +367,11 @@ EngineT<NW>::~EngineT() {
     skm_release();
     if (d_cnt_) cudaFree(d_cnt_);
     if (h_cnt_) cudaFreeHost(h_cnt_);
-    for (auto& e : ev_) if (e) cudaEventDestroy(e);
+    for (auto& q : ev_ring_) for (auto& e : q) if (e) cudaEventDestroy(e);
+    if (ev_dec_done_) cudaEventDestroy(ev_dec_done_);
+    if (ev_flush_) cudaEventDestroy(ev_flush_);
+    if (h_flush_) cudaFreeHost(h_flush_);
+    if (st_dec_) { cudaStreamSynchronize(st_dec_); cudaStreamDestroy(st_dec_); }
     if (ev_copy_) cudaEventDestroy(ev_copy_);
     if (st_copy_) cudaStreamDestroy(st_copy_);
     if (st_) cudaStreamDestroy(st_);

@@ -26,7 +26,6 @@ constexpr int SKM_APPLY_THREADS = 256;
 #endif
 constexpr int SKM_SLOTS = 1 << SKM_LOG2_SLOTS;                       // shared-memory table slots per CTA (32 B/slot at K<=63: 64 KB, 3 CTAs per SM)
 constexpr int SKM_SOFT_LIMIT = SKM_SLOTS - SKM_APPLY_THREADS - 64;   // claims stop here: the table can never fill up completely
-constexpr int SKM_TILE = 64;                                         // records staged in shared memory per tile
 constexpr int SKM_SIDE_RUNS = 16;
 constexpr int SKM_MAXW = 16;                                         // GPUs of one box
 
@@ -67,7 +66,7 @@ struct SkmSendArgs {
     int world, rank;
     int own_shift;            // >= 0: owner(b) = b >> own_shift (power-of-two split), else the generic range search
     u32 seg_idx, max_seg, bo_stride;
-    u64 cap_pair;
+    u64 cap_pair, epoch;
     const u32* segoff;        // [B] exclusive offsets of this chunk's blob (bucket-major), *total = record count
     const u64* total;
     u64* cursor;              // [world] records this GPU has already placed in owner o's region this epoch
@@ -102,6 +101,12 @@ __global__ void __launch_bounds__(256) k_skm_publish(SkmSendArgs a) {
         d.pad = 0;
         a.peer_ring[o][(u64)a.rank * a.max_seg + a.seg_idx] = d;
         a.peer_nseg[o][a.rank] = a.seg_idx + 1;
+        atomicMax((unsigned long long*)&a.counters[C_XUSED], (unsigned long long)(fits ? base + n : base));   // fullest region (host-side room checks)
+        if (o == 0) {
+            __threadfence();
+            a.counters[C_XEPOCH] = a.epoch;
+            atomicAdd((unsigned long long*)&a.counters[C_XSEGS], 1ull);
+        }
     }
     // the owner's slice of the offsets, relative to the blob: entry (b - lo) for its buckets, plus the end entry
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < (u64)a.n_buckets + a.world; i += (u64)gridDim.x * blockDim.x) {
@@ -251,13 +256,20 @@ struct SmemTable {
     }
 };
 
-// one aggregated k-mer -> the global table (find or claim, merge the saturating counters, keep the smallest rank)
+// One aggregated k-mer -> the global table.  A k-mer lives in exactly one bucket and a bucket is aggregated by one CTA at a time, so
+// when this call CLAIMS the slot nobody else can be touching its {payload, aux} words: they are written with one plain 16-byte store
+// (probe load -> claim CAS -> store: two dependent memory round trips per new key).  A key that already exists (earlier epoch: the
+// arena was flushed mid-stream) is merged with the same 64-bit CAS + atomicMin protocol every other writer uses.
 template <int NW>
 __device__ __forceinline__ bool table_merge(const Table<NW>& t, const Kmer<NW>& k, u64 agg, u64 rank) {
     bool claimed;
     u64 idx = table_find_or_claim(t, k, &claimed);
     Slot<NW>* s = t.slots + idx;
-    u64 cur = claimed ? PAYLOAD_FRESH : ldcg64(&s->payload);
+    if (claimed) {
+        stcg128(&s->payload, U128{agg, rank});
+        return true;
+    }
+    u64 cur = ldcg64(&s->payload);
     for (;;) {
         u64 nxt = payload_merge(cur, agg);
         if (nxt == cur) break;
@@ -266,7 +278,7 @@ __device__ __forceinline__ bool table_merge(const Table<NW>& t, const Kmer<NW>& 
         cur = old;
     }
     atomicMin(&s->aux, rank);
-    return claimed;
+    return false;
 }
 
 // the segments one aggregation launch reads, in device memory (built by k_skm_segs from what the senders published)
@@ -296,6 +308,9 @@ __global__ void __launch_bounds__(256) k_skm_segs(SkmFlushArgs a) {
         s_base[a.world] = acc;
         if (acc > (u32)SKM_MAX_SEGS) { atomicAdd(&a.counters[C_XERR], 1ull); acc = SKM_MAX_SEGS; }
         a.segs->n = acc;
+        a.counters[C_RESERVED] = a.counters[C_DISTINCT];   // keys the table already holds; the launch that follows adds its reservations
+        a.counters[C_DEFER] = 0;
+        a.counters[C_MAXU] = 0;
     }
     __syncthreads();
     for (int s = 0; s < a.world; s++) {
@@ -314,49 +329,55 @@ struct SkmApplyArgs {
     const SkmSegList* segs;
     const u32* bucket_list;   // nullptr: buckets 0 .. n_list-1; else the deferred buckets of the previous launch
     u32 n_list;
-    u32* next;                // dynamic bucket hand-out
     u64* counters;            // C_RESERVED: keys the table is committed to hold; C_DEFER / C_MAXU: deferred buckets, their largest bound
     u64 limit;
     u32* deferred;
 };
+constexpr u64 SKM_CREDIT = 1ull << 16;   // table room a CTA reserves at a time (keys)
 
-// One CTA per bucket (buckets handed out dynamically).  The bucket's records are staged through shared memory in tiles of SKM_TILE
-// (16-byte loads, coalesced per segment); an exclusive scan of their k-mer counts maps instance q of the tile to (record, position),
-// and every warp step takes 32 CONSECUTIVE instances, so all lanes are busy whatever the run lengths.
+__device__ __forceinline__ u64 shfl64(u64 v, int src) { return (u64)__shfl_sync(0xffffffffu, (unsigned long long)v, src); }
+
+// One CTA per bucket (static round-robin over the list: buckets are hash-uniform), one shared-memory table per CTA.  Inside a bucket
+// the WARPS run on their own: a warp loads 32 consecutive records of the bucket (one 32 / 48 B record per lane, coalesced), an
+// inclusive scan of their k-mer counts maps instance q of the batch to (record, position), and every warp step takes 32 CONSECUTIVE
+// instances -- all lanes busy whatever the run lengths -- fetching its record from the lane that holds it with shuffles.  No CTA-wide
+// barrier and no staging buffer inside a bucket; the next batch's records and the next bucket's segment ranges are loaded while the
+// current ones are processed.
 template <int NW>
 __global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply(Table<NW> tab, KParams<NW> kp, SkmApplyArgs a) {
-    constexpr int RW = NW + 2, PIECES = RW / 2;
-    extern __shared__ __align__(16) u64 s_dyn[];   // key[NW][S], pay[S], rnk[S], list[S] (u16), tile[SKM_TILE][RW]
+    constexpr int RW = NW + 2, WARPS = SKM_APPLY_THREADS / 32;
+    extern __shared__ __align__(16) u64 s_dyn[];   // key[NW][S], pay[S], rnk[S], list[S] (u16)
     __shared__ const u64* s_ptr[SKM_MAX_SEGS];
     __shared__ u32 s_cum[SKM_MAX_SEGS + 1];
-    __shared__ u32 s_P[SKM_TILE + 1];
-    __shared__ u32 s_warp[SKM_APPLY_THREADS / 32];
-    __shared__ u32 s_count, s_bucket, s_defer;
-    __shared__ unsigned s_new;
-    u64* tile = s_dyn + (NW + 2) * SKM_SLOTS + SKM_SLOTS / 4;
+    __shared__ u32 s_warp[WARPS];
+    __shared__ u32 s_count, s_defer;
+    __shared__ unsigned s_new, s_tot_new, s_tot_spill;
     SmemTable<NW> st{s_dyn, s_dyn + NW * SKM_SLOTS, s_dyn + (NW + 1) * SKM_SLOTS, reinterpret_cast<unsigned short*>(s_dyn + (NW + 2) * SKM_SLOTS), &s_count};
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned lane_le = 0xffffffffu >> (31 - lane);
     for (int i = tid; i < SKM_SLOTS; i += SKM_APPLY_THREADS) st.key[i] = EMPTY64;   // the flush re-empties what it merges
+    if (tid == 0) { s_tot_new = 0; s_tot_spill = 0; }
     const int n_segs = (int)a.segs->n;
+    const u32* my_so = tid < n_segs ? a.segs->segoff[tid] : nullptr;
+    const u64* my_recs = tid < n_segs ? a.segs->recs[tid] : nullptr;
     unsigned tot_new = 0, tot_spill = 0;
-    for (;;) {
+    u64 credit = 0;                      // thread 0: table room this CTA holds
+    u32 pos = blockIdx.x;
+    u32 nlo = 0, ncnt = 0;               // this thread's segment range of the NEXT bucket
+    if (pos < a.n_list && my_so) {
+        const u32 b = a.bucket_list ? a.bucket_list[pos] : pos;
+        nlo = my_so[b];
+        ncnt = my_so[b + 1] - nlo;
+    }
+    for (; pos < a.n_list; pos += gridDim.x) {
         __syncthreads();   // previous bucket fully flushed (and the empty table visible on the first trip)
-        if (tid == 0) {
-            const u32 i = atomicAdd(a.next, 1u);
-            s_bucket = i < a.n_list ? (a.bucket_list ? a.bucket_list[i] : i) : 0xFFFFFFFFu;
-            s_count = 0;
-            s_new = 0;
-        }
-        __syncthreads();
-        const u32 b = s_bucket;
-        if (b == 0xFFFFFFFFu) break;
-        // ---- the bucket's records: one range per segment
-        u32 cnt = 0;
-        if (tid < n_segs) {
-            const u32* so = a.segs->segoff[tid];
-            const u32 lo = so[b];
-            cnt = so[b + 1] - lo;
-            s_ptr[tid] = a.segs->recs[tid] + (u64)lo * RW;
+        const u32 cnt = ncnt;
+        if (my_so) s_ptr[tid] = my_recs + (u64)nlo * RW;
+        if (tid == 0) { s_count = 0; s_new = 0; }
+        if (pos + gridDim.x < a.n_list && my_so) {
+            const u32 nb = a.bucket_list ? a.bucket_list[pos + gridDim.x] : pos + gridDim.x;
+            nlo = my_so[nb];
+            ncnt = my_so[nb + 1] - nlo;
         }
         {
             u32 inc = cnt;
@@ -374,73 +395,98 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply(Table<NW> tab, 
         }
         __syncthreads();
         const u32 R = s_cum[n_segs];
-        // ---- room in the global table: every k-mer instance could be a new key
+        // ---- room in the global table: every k-mer instance could be a new key.  Credits are taken SKM_CREDIT keys at a time.
         if (tid == 0) {
+            bool defer = false;
             const u64 bound = (u64)R * SKM_MAX_RUN;
-            const u64 old = atomicAdd((unsigned long long*)&a.counters[C_RESERVED], (unsigned long long)bound);
-            const bool defer = R > 0 && old + bound > a.limit;
-            if (defer) {
-                atomicAdd((unsigned long long*)&a.counters[C_RESERVED], (unsigned long long)(0ull - bound));
-                a.deferred[atomicAdd((unsigned long long*)&a.counters[C_DEFER], 1ull)] = b;
-                atomicMax((unsigned long long*)&a.counters[C_MAXU], (unsigned long long)bound);
+            if (credit < bound) {
+                unsigned long long* res = (unsigned long long*)&a.counters[C_RESERVED];
+                const u64 want = bound - credit, ask = want > SKM_CREDIT ? want : SKM_CREDIT;
+                u64 old = atomicAdd(res, (unsigned long long)ask);
+                if (old + ask <= a.limit) credit += ask;
+                else {
+                    atomicAdd(res, (unsigned long long)(0ull - ask));
+                    bool got = false;
+                    if (ask != want) {
+                        old = atomicAdd(res, (unsigned long long)want);
+                        if (old + want <= a.limit) { credit += want; got = true; }
+                        else atomicAdd(res, (unsigned long long)(0ull - want));
+                    }
+                    if (!got) {
+                        defer = true;
+                        const u32 b = a.bucket_list ? a.bucket_list[pos] : pos;
+                        a.deferred[atomicAdd((unsigned long long*)&a.counters[C_DEFER], 1ull)] = b;
+                        atomicMax((unsigned long long*)&a.counters[C_MAXU], (unsigned long long)bound);
+                    }
+                }
             }
+            if (!defer) credit -= bound;
             s_defer = defer ? 1u : 0u;
         }
         __syncthreads();
-        if (s_defer || R == 0) continue;
+        if (s_defer || R == 0) {
+            if (tid == 0 && !s_defer) credit += (u64)R * SKM_MAX_RUN;
+            continue;
+        }
         unsigned my_new = 0;
-        for (u32 base = 0; base < R; base += SKM_TILE) {
-            const int nt = (int)(R - base < (u32)SKM_TILE ? R - base : (u32)SKM_TILE);
-            for (int p = tid; p < nt * PIECES; p += SKM_APPLY_THREADS) {
-                const int rec = p / PIECES, piece = p - rec * PIECES;
-                const u32 q = base + rec;
+        // ---- the warps: batches of 32 records, 32 consecutive instances per step
+        u64 nh = 0, nx[NW + 1];
+#pragma unroll
+        for (int i = 0; i < NW + 1; i++) nx[i] = 0;
+        auto load_rec = [&](u32 q) {
+            nh = 0;
+            if (q < R) {
                 int lo = 0, hi = n_segs;
                 while (hi - lo > 1) {
                     const int mid = (lo + hi) >> 1;
                     if (s_cum[mid] <= q) lo = mid; else hi = mid;
                 }
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(s_ptr[lo] + (u64)(q - s_cum[lo]) * RW) + piece);
-                reinterpret_cast<uint4*>(tile + rec * RW)[piece] = v;
-            }
-            __syncthreads();
-            if (tid < SKM_TILE) {   // whole warps: SKM_TILE is a multiple of 32
-                const u32 n = tid < nt ? (u32)skm_rec_n(tile[tid * RW]) : 0u;
-                u32 inc = n;
+                const uint4* p = reinterpret_cast<const uint4*>(s_ptr[lo] + (u64)(q - s_cum[lo]) * RW);
+                u64 w[RW];
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const u32 v = __shfl_up_sync(0xffffffffu, inc, d);
-                    if (lane >= d) inc += v;
+                for (int i = 0; i < RW / 2; i++) {
+                    const uint4 v = __ldg(p + i);
+                    w[2 * i] = (u64)v.x | ((u64)v.y << 32);
+                    w[2 * i + 1] = (u64)v.z | ((u64)v.w << 32);
                 }
-                if (lane == 31) s_warp[wid] = inc;
-                s_P[tid] = inc - n;
+                nh = w[0];
+#pragma unroll
+                for (int i = 0; i < NW + 1; i++) nx[i] = w[1 + i];
             }
-            __syncthreads();
-            if (tid < SKM_TILE && wid > 0) {
-                u32 off = 0;
-                for (int w = 0; w < wid; w++) off += s_warp[w];
-                s_P[tid] += off;
+        };
+        load_rec((u32)wid * 32u + lane);
+        for (u32 rb = (u32)wid * 32u; rb < R; rb += WARPS * 32) {
+            const u64 hdr = nh;
+            u64 x[NW + 1];
+#pragma unroll
+            for (int i = 0; i < NW + 1; i++) x[i] = nx[i];
+            load_rec(rb + WARPS * 32 + lane);                 // the next batch is in flight while this one is processed
+            const bool valid = rb + lane < R;
+            const u32 n = valid ? (u32)skm_rec_n(hdr) : 0u;
+            u32 inc = n;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 v = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += v;
             }
-            if (tid == 0) {
-                u32 tot = 0;
-                for (int w = 0; w < SKM_TILE / 32; w++) tot += s_warp[w];
-                s_P[SKM_TILE] = tot;
-            }
-            __syncthreads();
-            const u32 I = s_P[SKM_TILE];
-            for (u32 q0 = (u32)wid * 32u; q0 < I; q0 += SKM_APPLY_THREADS) {
+            const u32 I = __shfl_sync(0xffffffffu, inc, 31);
+            const u32 pe = inc - n;                            // first instance of this lane's record inside the batch
+            for (u32 q0 = 0; q0 < I; q0 += 32) {
                 const u32 q = q0 + lane;
                 const bool has = q < I;
+                // record of instance q: the record that holds q0, plus the records that start at window positions 1 .. lane
+                const unsigned starts = __reduce_or_sync(0xffffffffu, (valid && pe > q0 && pe - q0 < 32u) ? 1u << (pe - q0) : 0u);
+                const int first = __popc(__ballot_sync(0xffffffffu, valid && pe <= q0)) - 1;
+                const int src = (first + __popc(starts & lane_le)) & 31;
+                const int t = (int)(q - __shfl_sync(0xffffffffu, pe, src));
+                const u64 h = shfl64(hdr, src);
+                u64 y[NW + 1];
+#pragma unroll
+                for (int i = 0; i < NW + 1; i++) y[i] = shfl64(x[i], src);
                 const unsigned has_mask = __ballot_sync(0xffffffffu, has);
                 if (has) {
-                    const int rec = skm_pick_record(s_P, SKM_TILE, q);
-                    const int t = (int)(q - s_P[rec]);
-                    const u64* rp = tile + rec * RW;
-                    const u64 hdr = rp[0];
-                    u64 x[NW + 1];
-#pragma unroll
-                    for (int i = 0; i < NW + 1; i++) x[i] = rp[1 + i];
-                    const SkmInst<NW> in = skm_instance_rec<NW>(kp, hdr, x, t);
-                    const u64 rank = skm_rec_rank(hdr, t);
+                    const SkmInst<NW> in = skm_instance_rec<NW>(kp, h, y, t);
+                    const u64 rank = skm_rec_rank(h, t);
                     u32 slot;
                     const int state = st.find(tab, in.canon, in.left, in.right, rank, slot);
                     __syncwarp(has_mask);   // the lanes re-join before the counter update (see SmemTable)
@@ -453,8 +499,8 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply(Table<NW> tab, 
                 }
                 __syncwarp();
             }
-            __syncthreads();   // the tile and s_P are rewritten by the next trip
         }
+        __syncthreads();
         // ---- flush: one global update per distinct k-mer of the bucket, walking the claim list (every thread busy)
         const u32 n_claimed = s_count;
         for (u32 i = tid; i < n_claimed; i += SKM_APPLY_THREADS) {
@@ -468,15 +514,10 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply(Table<NW> tab, 
         if (my_new) atomicAdd(&s_new, my_new);
         tot_new += my_new;
         __syncthreads();
-        if (tid == 0) {   // give back what the bound over-reserved
-            const u64 bound = (u64)R * SKM_MAX_RUN;
-            atomicAdd((unsigned long long*)&a.counters[C_RESERVED], (unsigned long long)(0ull - (bound - (u64)s_new)));
-        }
+        if (tid == 0) credit += (u64)R * SKM_MAX_RUN - (u64)s_new;   // what the bound over-reserved stays with the CTA
     }
-    // per-CTA totals
-    __shared__ unsigned s_tot_new, s_tot_spill;
-    if (tid == 0) { s_tot_new = 0; s_tot_spill = 0; }
     __syncthreads();
+    if (tid == 0 && credit) atomicAdd((unsigned long long*)&a.counters[C_RESERVED], (unsigned long long)(0ull - credit));
     if (tot_new) atomicAdd(&s_tot_new, tot_new);
     if (tot_spill) atomicAdd(&s_tot_spill, tot_spill);
     __syncthreads();
@@ -489,7 +530,7 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply(Table<NW> tab, 
 // ------------------------------------------------------------------------------------------------ host side
 template <int NW>
 static constexpr size_t skm_apply_smem() {
-    return (size_t)(NW + 2) * SKM_SLOTS * sizeof(u64) + (size_t)SKM_SLOTS * sizeof(unsigned short) + (size_t)SKM_TILE * (NW + 2) * sizeof(u64);
+    return (size_t)(NW + 2) * SKM_SLOTS * sizeof(u64) + (size_t)SKM_SLOTS * sizeof(unsigned short);
 }
 static u64 next_pow2_u64(u64 x) { u64 p = 1; while (p < x) p <<= 1; return p; }
 
@@ -542,6 +583,14 @@ void EngineT<NW>::xchg_setup(uint64_t cap_records) {
     skm_init();
     const int world = prm_.world > 1 ? prm_.world : 1;
     if (xa_buf_.p) throw std::runtime_error("pgb200: exchange arena already set up");
+    if (!cap_records) {   // default: a fifth of the free HBM, at most 32 GB, split into the two epoch halves
+        create_table_if_needed();
+        size_t free_b = 0, total_b = 0;
+        PG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        u64 bytes = std::min<u64>((u64)free_b / 5, 32ull << 30);
+        if (const char* e = getenv("PGB200_SKM_ARENA_MB")) bytes = strtoull(e, nullptr, 0) << 20;
+        cap_records = bytes / ((NW + 2) * sizeof(u64)) / 2;
+    }
     u64 cap_pair = cap_records / world;
     if (cap_pair < 4096) cap_pair = 4096;
     u32 max_seg = SKM_MAX_SEGS / (world > 1 ? 1 : 1);
@@ -549,7 +598,7 @@ void EngineT<NW>::xchg_setup(uint64_t cap_records) {
     if (max_seg < 1) max_seg = 1;
     if (max_seg > (u32)SKM_MAX_SEGS) max_seg = SKM_MAX_SEGS;
     xa_geom_ = make_skm_arena_geom(world, skm_geom_.n_buckets, max_seg, cap_pair, NW + 2);
-    xa_halves_ = world > 1 ? 2 : 1;
+    xa_halves_ = 2;   // epoch parity: an epoch is aggregated (asynchronously) while the next one is being delivered
     xa_buf_.alloc(xa_geom_.half_bytes * xa_halves_);
     for (int h = 0; h < xa_halves_; h++)
         PG_CUDA(cudaMemsetAsync(static_cast<char*>(xa_buf_.p) + h * xa_geom_.half_bytes, 0, xa_geom_.off_recs, st_));   // nseg, ring, offsets
@@ -559,6 +608,7 @@ void EngineT<NW>::xchg_setup(uint64_t cap_records) {
     xa_send_epoch_ = 0;
     xa_seg_idx_ = 0;
     xa_flushed_epoch_ = 0;
+    xa_reads_cum_.assign(1, 0);
     if (prm_.verbose) fprintf(stderr, "[pgb200] exchange arena: %d x %.2f GB (%llu records per sender, %u segments per sender and epoch)\n", xa_halves_,
                               xa_geom_.half_bytes / 1e9, (unsigned long long)cap_pair, max_seg);
 }
@@ -599,12 +649,7 @@ template <int NW>
 void EngineT<NW>::xchg_default_setup() {
     if (xa_buf_.p) return;
     if (prm_.world > 1) throw std::runtime_error("pgb200: multi-GPU engines need pgb200_xchg_setup + xchg_import before the first chunk");
-    create_table_if_needed();
-    size_t free_b = 0, total_b = 0;
-    PG_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    u64 bytes = std::min<u64>((u64)free_b / 6, 16ull << 30);
-    if (const char* e = getenv("PGB200_SKM_ARENA_MB")) bytes = strtoull(e, nullptr, 0) << 20;
-    xchg_setup(bytes / ((NW + 2) * sizeof(u64)));
+    xchg_setup(0);
 }
 
 template <int NW>
@@ -616,6 +661,7 @@ void EngineT<NW>::skm_send_args(void* out_args, int half) {
     a.rank = prm_.rank;
     a.own_shift = skm_own_shift_;
     a.seg_idx = xa_seg_idx_;
+    a.epoch = xa_send_epoch_ + 1;   // 0 = nothing published yet
     a.max_seg = xa_geom_.max_seg;
     a.bo_stride = xa_geom_.bo_max + 1;
     a.cap_pair = xa_geom_.cap_pair;
@@ -636,24 +682,49 @@ void EngineT<NW>::skm_send_args(void* out_args, int half) {
     a.counters = d_cnt_;
 }
 
-// Room for the next chunk's records and segment (called OUTSIDE the caller's per-chunk event bracket: a flush times itself).
-// Single GPU: decided here.  Several GPUs: the caller fences + flushes all GPUs collectively; running out of room is an error.
+// Upper estimate of the fullest arena region's fill once a chunk of n_rec more reads has been partitioned.  What the host knows
+// (C_XUSED after C_XSEGS segments of epoch C_XEPOCH) lags behind the stream; the chunks it does not know yet are assumed to make
+// twice the records per read seen so far in this epoch -- before anything has been seen: four times a run every w/4 k-mers, runs being
+// about w/3 long on random sequence -- and never more than one record per k-mer.  An estimate that turns out too low is caught on the
+// device: k_skm_publish refuses the blob and raises C_XERR (an error, not a wrong result).
+template <int NW>
+u64 EngineT<NW>::skm_room_estimate(u64 n_rec) {
+    const u64 per_read_worst = (u64)std::max(1, prm_.max_rd_len - prm_.K + 1);
+    const bool current = h_cnt_[C_XEPOCH] == xa_send_epoch_ + 1;
+    u64 segs_done = current ? h_cnt_[C_XSEGS] : 0, used = current ? h_cnt_[C_XUSED] : 0;
+    if (xa_reads_cum_.empty()) xa_reads_cum_.push_back(0);
+    if (segs_done >= xa_reads_cum_.size()) segs_done = xa_reads_cum_.size() - 1;
+    const u64 reads_done = xa_reads_cum_[segs_done], reads_fed = xa_reads_cum_.back();
+    u64 per_read = 4 * (per_read_worst / (u64)std::max(1, skm_geom_.w / 4) + 1);
+    if (reads_done) per_read = std::max<u64>(1, (2 * used * (u64)xa_geom_.world + reads_done - 1) / reads_done);   // `used` is ONE region's fill
+    per_read = std::min(per_read, per_read_worst);
+    return used + ((reads_fed - reads_done + n_rec) * per_read + xa_geom_.world - 1) / xa_geom_.world;
+}
+
+// Room for the next chunk's records and segment (called OUTSIDE the caller's per-chunk event bracket: an aggregation times itself).
+// Single GPU: decided here; the aggregation launch is asynchronous (it is ordered behind the scatter kernels by the stream, and
+// the next chunks go to the other arena half).  Several GPUs: the caller fences + flushes all GPUs collectively (pgb200_xchg_room).
 template <int NW>
 void EngineT<NW>::skm_make_room(u64 n_rec, bool host_text) {
     skm_init();
     xchg_default_setup();
-    const u64 worst = n_rec * (u64)std::max(1, prm_.max_rd_len - prm_.K + 1);   // every k-mer its own record
     if (xa_geom_.world == 1) {
-        const u64 known = h_cnt_[C_XUSED];   // records in the arena as of the previous chunk (arrived with this chunk's host sync)
         const int every = skm_flush_every_ >= 0 ? skm_flush_every_ : (host_text ? 4 : 0);
-        const bool full = xa_seg_idx_ >= xa_geom_.max_seg || known + worst > xa_geom_.cap_pair;
+        const bool full = xa_seg_idx_ >= xa_geom_.max_seg || skm_room_estimate(n_rec) > xa_geom_.cap_pair;
         if ((full || (every > 0 && xa_seg_idx_ >= (u32)every)) && xa_seg_idx_ > 0) {
-            skm_fence();
+            skm_close_epoch(false);
             skm_flush();
         }
     } else if (xa_seg_idx_ >= xa_geom_.max_seg) {
         throw std::runtime_error("pgb200: too many chunks in one exchange epoch: call pgb200_xchg_fence + pgb200_flush (on all GPUs) more often");
     }
+}
+
+// several GPUs: the coordinator asks before it feeds the next chunk
+template <int NW>
+bool EngineT<NW>::xchg_room(uint64_t n_rec) {
+    if (!xa_buf_.p) return true;
+    return xa_seg_idx_ < xa_geom_.max_seg && skm_room_estimate(n_rec) <= xa_geom_.cap_pair;
 }
 
 // partition the chunk just decoded and deliver its records (inside the caller's "insert" event bracket)
@@ -662,7 +733,6 @@ void EngineT<NW>::skm_feed_chunk(size_t ci) {
     const ReadChunk& ch = chunks_[ci];
     const u32 B = skm_geom_.n_buckets;
     const int world = xa_geom_.world;
-    (void)world;
     PG_CUDA(cudaMemsetAsync(skm_cnt_.p, 0, (B + 1) * sizeof(u32), st_));
     PG_CUDA(cudaMemsetAsync(skm_cursor_.p, 0, (B + 1) * sizeof(u32), st_));
     const size_t ring = (size_t)skm_part_threads_ * 2 * skm_geom_.w * sizeof(u32);
@@ -683,50 +753,48 @@ void EngineT<NW>::skm_feed_chunk(size_t ci) {
     PG_CUDA(cudaGetLastError());
     k_skm_rescan<NW><<<blocks, skm_part_threads_, ring, st_>>>(a, skm_geom_, ch.words, ch.len, ch.n_rec, W64_, ch.ord_base, ch.ord_stride, nruns, cursor_b);
     PG_CUDA(cudaGetLastError());
-    // the sender cursor travels to the host with the NEXT chunk's one sync (C_XUSED), so the room check above lags by one chunk
-    PG_CUDA(cudaMemcpyAsync(d_cnt_ + C_XUSED, misc, sizeof(u64), cudaMemcpyDeviceToDevice, st_));
+    if (xa_reads_cum_.empty()) xa_reads_cum_.push_back(0);
+    xa_reads_cum_.push_back(xa_reads_cum_.back() + ch.n_rec);
     xa_seg_idx_++;
     xa_dirty_ = true;
     p1_.launches += 7;
 }
 
-// every record this GPU produced in the current epoch has reached its owner; the next chunks go to the other arena half
+// Close the current exchange epoch: the chunks fed from now on go to the other arena half.
+//   hard (pgb200_xchg_fence; several GPUs: before the caller's barrier): waits until every record this GPU produced has reached its
+//        owner, books the chunk timings, raises decode / arena errors;
+//   soft (single GPU, mid-stream): nothing to wait for -- the aggregation launch is stream-ordered behind the scatter kernels.
+// Either way the previous aggregation (it read the half that is about to be written again) is completed first.
 template <int NW>
-void EngineT<NW>::skm_fence() {
-    settle_timing();
-    sync();
-    read_counters();
-    check_format_counter();
-    if (h_cnt_[C_XERR])
-        throw std::runtime_error("pgb200: exchange arena overflow (records of a chunk did not fit their owner's region, or too many segments): "
-                                 "raise the arena capacity (pgb200_xchg_setup / PGB200_SKM_ARENA_MB) or flush more often");
+void EngineT<NW>::skm_close_epoch(bool hard) {
+    if (hard) {
+        settle_timing();
+        read_counters();
+        check_format_counter();
+        if (h_cnt_[C_XERR])
+            throw std::runtime_error("pgb200: exchange arena overflow (records of a chunk did not fit their owner's region, or too many segments): "
+                                     "raise the arena capacity (pgb200_xchg_setup / PGB200_SKM_ARENA_MB) or flush more often");
+    }
     if (!xa_buf_.p) return;
+    skm_flush_complete();
     if (xa_dirty_ || prm_.world > 1) {
         xa_send_epoch_++;
         xa_seg_idx_ = 0;
-        h_cnt_[C_XUSED] = 0;
+        xa_reads_cum_.assign(1, 0);
         xa_dirty_ = false;
-        PG_CUDA(cudaMemsetAsync(skm_misc_.p, 0, 16 * sizeof(u64), st_));   // sender cursors
+        PG_CUDA(cudaMemsetAsync(skm_misc_.p, 0, 16 * sizeof(u64), st_));          // sender cursors
         PG_CUDA(cudaMemsetAsync(d_cnt_ + C_XUSED, 0, sizeof(u64), st_));
+        PG_CUDA(cudaMemsetAsync(d_cnt_ + C_XSEGS, 0, sizeof(u64), st_));
     }
 }
-
-// aggregate the fenced epoch into the global table (several GPUs: only after every GPU has fenced -- the caller's barrier)
 template <int NW>
-void EngineT<NW>::skm_flush() {
-    if (!xa_buf_.p || xa_flushed_epoch_ >= xa_send_epoch_) return;
-    if (xa_flushed_epoch_ + 1 != xa_send_epoch_) throw std::runtime_error("pgb200: internal: more than one unflushed exchange epoch");
-    const int half = (int)(xa_flushed_epoch_ % xa_halves_);
-    char* hb = static_cast<char*>(xa_buf_.p) + (u64)half * xa_geom_.half_bytes;
-    PG_CUDA(cudaEventRecord(ev_skm_[0], st_));
-    create_table_if_needed();
-    read_counters();
+void EngineT<NW>::skm_fence() { skm_close_epoch(true); }
+
+template <int NW>
+void EngineT<NW>::skm_launch_apply(const u32* list, u32 n_list, u32* deferred_out) {
     u64* misc = skm_misc_.template as<u64>();
     SkmSegList* segs = reinterpret_cast<SkmSegList*>(reinterpret_cast<char*>(misc) + 4096);
-    const u32 n_owned = skm_own_hi_ - skm_own_lo_;
-    u32* deferred[2] = {reinterpret_cast<u32*>(reinterpret_cast<char*>(segs) + sizeof(SkmSegList)), nullptr};
-    deferred[1] = deferred[0] + n_owned + 1;
-    u32* d_next = reinterpret_cast<u32*>(misc + 48);
+    char* hb = static_cast<char*>(xa_buf_.p) + (u64)xa_flush_half_ * xa_geom_.half_bytes;
     SkmFlushArgs fa;
     fa.world = xa_geom_.world; fa.max_seg = xa_geom_.max_seg; fa.bo_stride = xa_geom_.bo_max + 1; fa.cap_pair = xa_geom_.cap_pair; fa.rec_words = NW + 2;
     fa.nseg = reinterpret_cast<const u32*>(hb + xa_geom_.off_nseg);
@@ -735,61 +803,94 @@ void EngineT<NW>::skm_flush() {
     fa.recs = reinterpret_cast<const u64*>(hb + xa_geom_.off_recs);
     fa.segs = segs;
     fa.counters = d_cnt_;
-    k_skm_segs<<<1, 256, 0, st_>>>(fa);
+    k_skm_segs<<<1, 256, 0, st_>>>(fa);   // segment list + C_RESERVED = keys in the table, C_DEFER = C_MAXU = 0
     PG_CUDA(cudaGetLastError());
-    const size_t smem = skm_apply_smem<NW>();
-    const u32* list = nullptr;
-    u32 n_list = n_owned;
-    int launches = 0, which = 0;
-    for (;;) {
-        const u64 have = h_cnt_[C_DISTINCT];
-        u64 zero3[3] = {have, 0, 0};   // C_RESERVED, C_DEFER, C_MAXU are consecutive
-        PG_CUDA(cudaMemcpyAsync(d_cnt_ + C_RESERVED, zero3, sizeof zero3, cudaMemcpyHostToDevice, st_));
-        PG_CUDA(cudaMemsetAsync(d_next, 0, sizeof(u32), st_));
-        SkmApplyArgs aa;
-        aa.segs = segs; aa.bucket_list = list; aa.n_list = n_list; aa.next = d_next; aa.counters = d_cnt_;
-        aa.limit = (u64)(0.85 * (double)cap_);
-        aa.deferred = deferred[which];
-        const unsigned blocks = (unsigned)std::min<u64>((u64)n_list, 148ull * (NW == 2 ? 3 : 2));
-        if (blocks) k_skm_apply<NW><<<blocks, SKM_APPLY_THREADS, smem, st_>>>(tab_, kp_, aa);
-        PG_CUDA(cudaGetLastError());
-        p1_.launches += 1;
-        launches++;
+    SkmApplyArgs aa;
+    aa.segs = segs; aa.bucket_list = list; aa.n_list = n_list; aa.counters = d_cnt_;
+    aa.limit = (u64)(0.85 * (double)cap_);
+    aa.deferred = deferred_out;
+    const unsigned blocks = (unsigned)std::min<u64>((u64)n_list, 148ull * (NW == 2 ? 3 : 2));
+    if (blocks) k_skm_apply<NW><<<blocks, SKM_APPLY_THREADS, skm_apply_smem<NW>(), st_>>>(tab_, kp_, aa);
+    PG_CUDA(cudaGetLastError());
+    PG_CUDA(cudaMemcpyAsync(h_flush_, d_cnt_ + C_XERR, 5 * sizeof(u64), cudaMemcpyDeviceToHost, st_));   // XERR, XUSED, RESERVED, DEFER, MAXU
+    p1_.launches += 2;
+}
+
+// Aggregate the closed epoch into the global table (several GPUs: only after every GPU has fenced -- the caller's barrier).
+// Returns as soon as the work is queued; skm_flush_complete (next epoch close, pgb200_finish_pass1) reads the outcome.
+template <int NW>
+void EngineT<NW>::skm_flush() {
+    if (!xa_buf_.p || xa_flushed_epoch_ >= xa_send_epoch_) return;
+    skm_flush_complete();
+    if (xa_flushed_epoch_ + 1 != xa_send_epoch_) throw std::runtime_error("pgb200: internal: more than one unflushed exchange epoch");
+    create_table_if_needed();
+    xa_flush_half_ = (int)(xa_flushed_epoch_ % xa_halves_);
+    PG_CUDA(cudaEventRecord(ev_skm_[0], st_));
+    const u32 n_owned = skm_own_hi_ - skm_own_lo_;
+    u32* deferred0 = reinterpret_cast<u32*>(skm_misc_.template as<char>() + 4096 + sizeof(SkmSegList));
+    skm_launch_apply(nullptr, n_owned, deferred0);
+    PG_CUDA(cudaEventRecord(ev_flush_, st_));
+    xa_flush_inflight_ = true;
+}
+
+template <int NW>
+void EngineT<NW>::skm_flush_complete() {
+    if (!xa_flush_inflight_) return;
+    xa_flush_inflight_ = false;
+    PG_CUDA(cudaEventSynchronize(ev_flush_));
+    float ms;
+    PG_CUDA(cudaEventElapsedTime(&ms, ev_skm_[0], ev_flush_));
+    const u32 n_owned = skm_own_hi_ - skm_own_lo_;
+    u32* deferred[2];
+    deferred[0] = reinterpret_cast<u32*>(skm_misc_.template as<char>() + 4096 + sizeof(SkmSegList));
+    deferred[1] = deferred[0] + n_owned + 1;
+    int launches = 1, which = 0;
+    u64 n_def = h_flush_[3], maxu = h_flush_[4];
+    if (h_flush_[0]) throw std::runtime_error("pgb200: too many segments in one exchange epoch (flush more often)");
+    while (n_def) {
+        // buckets whose worst case did not fit the table: grow so that (at least) the largest one fits, run them again
         read_counters();
-        if (h_cnt_[C_XERR]) throw std::runtime_error("pgb200: too many segments in one exchange epoch (flush more often)");
-        const u64 n_def = h_cnt_[C_DEFER];
-        if (!n_def) break;
-        // grow so that (at least) the largest deferred bucket fits, then run the deferred buckets again
         u64 cap = cap_ * 2;
-        while (0.85 * (double)cap < (double)(h_cnt_[C_DISTINCT] + h_cnt_[C_MAXU])) cap <<= 1;
+        while (0.85 * (double)cap < (double)(h_cnt_[C_DISTINCT] + maxu)) cap <<= 1;
         size_t free_b = 0, total_b = 0;
         PG_CUDA(cudaMemGetInfo(&free_b, &total_b));
         if (cap * sizeof(Slot<NW>) + (1ull << 28) > free_b)
             throw std::runtime_error("pgb200: k-mer table cannot grow further (out of HBM); use more GPUs");
         grow_table(cap);
-        list = deferred[which];
-        n_list = (u32)n_def;
+        PG_CUDA(cudaEventRecord(ev_skm_[0], st_));
+        skm_launch_apply(deferred[which], (u32)n_def, deferred[which ^ 1]);
+        PG_CUDA(cudaEventRecord(ev_flush_, st_));
+        PG_CUDA(cudaEventSynchronize(ev_flush_));
+        float ms2;
+        PG_CUDA(cudaEventElapsedTime(&ms2, ev_skm_[0], ev_flush_));
+        ms += ms2;
         which ^= 1;
+        launches++;
+        n_def = h_flush_[3];
+        maxu = h_flush_[4];
     }
     // the epoch's half is free again: senders may use it from the epoch after next
+    char* hb = static_cast<char*>(xa_buf_.p) + (u64)xa_flush_half_ * xa_geom_.half_bytes;
     PG_CUDA(cudaMemsetAsync(hb + xa_geom_.off_nseg, 0, (size_t)xa_geom_.world * sizeof(u32), st_));
-    PG_CUDA(cudaEventRecord(ev_skm_[1], st_));
-    PG_CUDA(cudaEventSynchronize(ev_skm_[1]));
-    float ms;
-    PG_CUDA(cudaEventElapsedTime(&ms, ev_skm_[0], ev_skm_[1]));
     p1_.ms_insert += ms;
     p1_.ms_apply += ms;
     xa_flushed_epoch_++;
     if (prm_.verbose >= 2 || getenv("PGB200_SKM_STATS"))
-        fprintf(stderr, "[pgb200] aggregated epoch %llu: %u owned bucket(s), %d launch(es), %.2f ms; %llu instance(s) spilled past the shared-memory tables; %llu distinct, table %llu slots\n",
-                (unsigned long long)xa_flushed_epoch_, n_owned, launches, ms, (unsigned long long)h_cnt_[C_MISC2], (unsigned long long)h_cnt_[C_DISTINCT], (unsigned long long)cap_);
+        fprintf(stderr, "[pgb200] aggregated epoch %llu: %u owned bucket(s), %d launch(es), %.2f ms, table %llu slots\n", (unsigned long long)xa_flushed_epoch_, n_owned,
+                launches, ms, (unsigned long long)cap_);
 }
 
 template <int NW>
 void EngineT<NW>::skm_reset() {
     // single GPU: nothing of the arena survives a reset; several GPUs: the epochs keep alternating (peers may already deliver)
-    if (xa_buf_.p && prm_.world <= 1) {
-        if (xa_dirty_) { skm_fence(); xa_flushed_epoch_ = xa_send_epoch_; PG_CUDA(cudaMemsetAsync(static_cast<char*>(xa_buf_.p) + xa_geom_.off_nseg, 0, sizeof(u32), st_)); }
+    if (!xa_buf_.p) return;
+    sync();
+    skm_flush_complete();
+    if (prm_.world <= 1 && (xa_dirty_ || xa_flushed_epoch_ != xa_send_epoch_)) {
+        skm_close_epoch(false);
+        for (int h = 0; h < xa_halves_; h++)
+            PG_CUDA(cudaMemsetAsync(static_cast<char*>(xa_buf_.p) + (u64)h * xa_geom_.half_bytes + xa_geom_.off_nseg, 0, sizeof(u32), st_));
+        xa_flushed_epoch_ = xa_send_epoch_;
     }
 }
 
@@ -811,7 +912,12 @@ void EngineT<NW>::skm_release() {
     template void EngineT<NW>::skm_send_args(void*, int);                    \
     template void EngineT<NW>::skm_feed_chunk(size_t);                       \
     template void EngineT<NW>::skm_make_room(u64, bool);                     \
+    template bool EngineT<NW>::xchg_room(uint64_t);                          \
     template void EngineT<NW>::skm_fence();                                  \
+    template void EngineT<NW>::skm_close_epoch(bool);                        \
+    template void EngineT<NW>::skm_flush_complete();                         \
+    template void EngineT<NW>::skm_launch_apply(const u32*, u32, u32*);      \
+    template u64 EngineT<NW>::skm_room_estimate(u64);                        \
     template void EngineT<NW>::skm_flush();                                  \
     template void EngineT<NW>::skm_reset();                                  \
     template void EngineT<NW>::skm_release();

@@ -202,3 +202,84 @@ def scenario_adversarial(d: str, seed=9, crlf=False, K_hint=31) -> str:
     cfg = os.path.join(d, "adv.cfg")
     write_config(cfg, 100, [{"avg_ins": 200, "files": [("f", fa), ("q", fq)]}])
     return cfg
+
+
+# ---------------------------------------------------------------- vectorised writers for the config-sized cases (millions of reads)
+def _names(n: int, tag: bytes, width: int = 9) -> np.ndarray:
+    ids = np.arange(n, dtype=np.int64)
+    out = np.empty((n, len(tag) + width), dtype=np.uint8)
+    out[:, :len(tag)] = np.frombuffer(tag, dtype=np.uint8)
+    for d in range(width):
+        out[:, len(tag) + width - 1 - d] = (ids // 10 ** d) % 10 + 48
+    return out
+
+
+def write_fastq_fast(path: str, reads: np.ndarray, tag: str = "r") -> None:
+    n, L = reads.shape
+    nm = _names(n, b"@" + tag.encode())
+    rec = np.empty((n, nm.shape[1] + 1 + L + 3 + L + 1), dtype=np.uint8)
+    o = nm.shape[1]
+    rec[:, :o] = nm
+    rec[:, o] = 10
+    rec[:, o + 1:o + 1 + L] = reads
+    rec[:, o + 1 + L] = 10
+    rec[:, o + 2 + L] = ord("+")
+    rec[:, o + 3 + L] = 10
+    rec[:, o + 4 + L:o + 4 + 2 * L] = ord("I")
+    rec[:, o + 4 + 2 * L] = 10
+    rec.tofile(path)
+    _pad_if_32k(path)
+
+
+def write_fasta_fast(path: str, reads: np.ndarray, tag: str = "r") -> None:
+    n, L = reads.shape
+    nm = _names(n, b">" + tag.encode())
+    rec = np.empty((n, nm.shape[1] + 1 + L + 1), dtype=np.uint8)
+    o = nm.shape[1]
+    rec[:, :o] = nm
+    rec[:, o] = 10
+    rec[:, o + 1:o + 1 + L] = reads
+    rec[:, o + 1 + L] = 10
+    rec.tofile(path)
+    _pad_if_32k(path)
+
+
+def config_c1(d: str, genome_len=4_600_000, coverage=30, seed=1) -> str:
+    """BASELINE.json configs[0]: E. coli-sized genome, one library, 100 bp SE single-line FASTA, err 0.5 %, K=31."""
+    g = genome(genome_len, seed)
+    n = genome_len * coverage // 100
+    write_fasta_fast(os.path.join(d, "c1.fa"), se_reads(g, n, 100, 0.005, seed + 100), "e")
+    cfg = os.path.join(d, "c1.cfg")
+    write_config(cfg, 100, [{"avg_ins": 200, "files": [("f", os.path.join(d, "c1.fa"))]}])
+    return cfg
+
+
+def config_c2(d: str, genome_len=10_000_000, coverage=30, seed=42) -> str:
+    """BASELINE.json configs[1] shape at a size the reference finishes in about a minute: 150 bp PE FASTQ q1/q2, insert 300, err 0.1 %."""
+    g = genome(genome_len, seed)
+    r1, r2 = pe_reads(g, genome_len * coverage // 300, 150, 300, 0.001, seed + 1)
+    write_fastq_fast(os.path.join(d, "c2_1.fq"), r1, "p")
+    write_fastq_fast(os.path.join(d, "c2_2.fq"), r2, "p")
+    cfg = os.path.join(d, "c2.cfg")
+    write_config(cfg, 150, [{"avg_ins": 300, "files": [("q1", os.path.join(d, "c2_1.fq")), ("q2", os.path.join(d, "c2_2.fq"))]}])
+    return cfg
+
+
+def config_c5(d: str, genome_len=20_000_000, seed=5) -> str:
+    """BASELINE.json configs[4]: three libraries -- rank1 avg_ins=200 q1/q2 150 bp; rank2 avg_ins=500 f1/f2 100 bp
+    FASTA; rank3 avg_ins=2000 reverse_seq=1 asm_flags=3 f= + q= SE -- about 30x in total, planted repeats so the graph branches."""
+    g = genome(genome_len, seed, repeat=(3000, 6))
+    j = lambda n: os.path.join(d, n)
+    a1, a2 = pe_reads(g, genome_len * 15 // 300, 150, 200 + 100, 0.002, seed + 1)
+    write_fastq_fast(j("c5_a1.fq"), a1, "a"); write_fastq_fast(j("c5_a2.fq"), a2, "a")
+    b1, b2 = pe_reads(g, genome_len * 10 // 200, 100, 500, 0.002, seed + 2)
+    write_fasta_fast(j("c5_b1.fa"), b1, "b"); write_fasta_fast(j("c5_b2.fa"), b2, "b")
+    write_fasta_fast(j("c5_c.fa"), se_reads(g, genome_len * 3 // 100, 100, 0.002, seed + 3), "c")
+    write_fastq_fast(j("c5_d.fq"), se_reads(g, genome_len * 2 // 120, 120, 0.002, seed + 4), "d")
+    cfg = j("c5.cfg")
+    write_config(cfg, 150, [
+        {"avg_ins": 200, "files": [("q1", j("c5_a1.fq")), ("q2", j("c5_a2.fq"))]},
+        {"avg_ins": 500, "files": [("f1", j("c5_b1.fa")), ("f2", j("c5_b2.fa"))]},
+        {"avg_ins": 2000, "reverse_seq": 1, "asm_flags": 3, "files": [("f", j("c5_c.fa")), ("q", j("c5_d.fq"))]},
+    ])
+    return cfg

@@ -48,6 +48,6 @@ def test_all_pipeline_in_one_process(tmp_path):
     outs = {}
     for tag, exe in (("ref", util.REF63), ("gpu", B63)):
         out = str(tmp_path / tag)
-        util.run([exe, "all", "-s", cfg, "-K", "31", "-p", "1", "-a", "1", "-R", "-o", out], timeout=900)
+        util.run([exe, "all", "-s", cfg, "-K", "31", "-p", "1", "-a", "1", "-R", "-o", out], timeout=240)
         outs[tag] = out
     util.compare(outs["ref"], outs["gpu"], util.SUFFIXES_R + ["contig", "Arc", "updated.edge", "ContigIndex", "scafSeq", "scaf", "links", "newContigIndex"])

@@ -111,3 +111,24 @@ def test_two_gpu_one_process(tmp_path):
     _check(out, kmerfreq, want)
     for e in engs:
         e.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("gpus", [2, "all"])
+def test_cli_multi_gpu_byte_identical(tmp_path, gpus):
+    """configs[4] shape through the unchanged CLI with pass 1 sharded over the GPUs (PGB200_GPUS): all seven files and the
+    reference's own `contig` outputs must equal the unmodified reference binary's; tiny chunks so that every GPU gets many."""
+    import subprocess
+    if not util.have_ref():
+        pytest.skip("oracle/_ref not shipped")
+    cfg = synth.scenario_multilib(str(tmp_path))
+    ref, gpu = str(tmp_path / "ref"), str(tmp_path / "gpu")
+    util.run_ref(util.REF63, cfg, ref, 63, 8, ("-a", "1", "-R"))
+    env = dict(os.environ, PGB200_GPUS=str(gpus), PGB200_CHUNK_MB="1", PGB200_VERBOSE="1")
+    r = subprocess.run([api.BIN63, "pregraph", "-s", cfg, "-K", "63", "-p", "8", "-a", "1", "-R", "-o", gpu], capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, r.stderr[-4000:]
+    assert "pass 1 sharded over" in r.stderr
+    util.compare(ref, gpu, util.SUFFIXES_R)
+    for pre in (ref, gpu):
+        util.run([util.REF63, "contig", "-g", pre, "-R"])
+    util.compare(ref, gpu, ["contig", "Arc", "updated.edge", "ContigIndex"])

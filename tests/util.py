@@ -23,7 +23,11 @@ def build_oracle():
 
 
 def run(cmd, timeout=600):
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    except subprocess.TimeoutExpired as ex:   # show where it hung
+        err = ex.stderr.decode(errors="replace") if isinstance(ex.stderr, bytes) else (ex.stderr or "")
+        raise AssertionError(f"{' '.join(cmd)}\ntimed out after {timeout} s; stderr tail:\n{err[-3000:]}")
     assert r.returncode == 0, f"{' '.join(cmd)}\nrc={r.returncode}\n{r.stderr[-4000:]}"
     return r.stderr
 
