@@ -67,18 +67,50 @@ struct TileBaseOut {
 
 // newline number g (0-based) at byte `pos`: it ends line g and line g+1 starts at pos+1.  Records are lpr = 1 << lshift lines long:
 // line 0 of a record is its header, line 1 its sequence, FASTQ line 2 the '+' separator.
+struct LineIndexCtx {
+    const unsigned char* bytes;
+    u64 nbytes, n_rec;
+    u32* seq_start;
+    u32* seq_end;
+    int lshift;
+    unsigned lmask;
+    unsigned char hdr;
+};
+__device__ __forceinline__ unsigned line_index_one(const LineIndexCtx& c, u64 pos, u64 g) {
+    unsigned bad = 0;
+    if (((unsigned)g & c.lmask) == 1u) {
+        const u64 r = g >> c.lshift;
+        if (r < c.n_rec) c.seq_end[r] = (u32)pos;
+    }
+    const u64 g1 = g + 1;
+    const unsigned ph = (unsigned)g1 & c.lmask;
+    if (ph == 1u) {
+        const u64 r = g1 >> c.lshift;
+        if (r < c.n_rec) c.seq_start[r] = (u32)(pos + 1);
+    } else if (pos + 1 < c.nbytes) {
+        if (ph == 0u) { if ((g1 >> c.lshift) < c.n_rec && c.bytes[pos + 1] != c.hdr) bad++; }
+        else if (ph == 2u && c.bytes[pos + 1] != '+') bad++;     // only reached for FASTQ (lmask == 3)
+    }
+    return bad;
+}
+
+// One warp per 2 KB tile.  A lane finds 0.2 newlines per 16-byte group on FASTQ text, so the newlines of a tile are first compacted
+// into a per-warp queue (their order = their global line numbers) and then handled 32 at a time, all lanes busy.
+constexpr int LI_QUEUE = 160, LI_BURST = 64;
 __global__ void __launch_bounds__(256) k_line_index(const uint4* __restrict__ text, u64 nbytes, u64 n_tiles, const u32* __restrict__ tile_base, int lshift,
                                                     u64 n_rec, u32* __restrict__ seq_start, u32* __restrict__ seq_end, u64* counters) {
-    const int lane = threadIdx.x & 31;
+    __shared__ u32 s_q[8][LI_QUEUE];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const u64 warp0 = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
     const u64 n_groups = (nbytes + 15) / 16;
-    const unsigned lmask = (1u << lshift) - 1u;
-    const unsigned char* bytes = reinterpret_cast<const unsigned char*>(text);
-    const unsigned char hdr = lshift == 2 ? '@' : '>';
+    LineIndexCtx c{reinterpret_cast<const unsigned char*>(text), nbytes, n_rec, seq_start, seq_end, lshift, (1u << lshift) - 1u, (unsigned char)(lshift == 2 ? '@' : '>')};
+    u32* q = s_q[wib];
     unsigned bad = 0;
-    if (warp0 == 0 && lane == 0 && nbytes && bytes[0] != hdr) bad++;
+    if (warp0 == 0 && lane == 0 && nbytes && c.bytes[0] != c.hdr) bad++;
     for (u64 tile = warp0; tile < n_tiles; tile += nwarps) {
-        u64 g0 = tile_base[tile];
+        u64 gq = tile_base[tile];     // global line number of the first queued newline
+        unsigned qn = 0;              // queued newlines (warp-uniform)
+        const u64 tile_byte0 = tile * NL_TILE;
         unsigned m[NL_ITERS];
 #pragma unroll
         for (int it = 0; it < NL_ITERS; it++) {
@@ -87,37 +119,46 @@ __global__ void __launch_bounds__(256) k_line_index(const uint4* __restrict__ te
         }
 #pragma unroll
         for (int it = 0; it < NL_ITERS; it++) {
-            const unsigned c = __popc(m[it]);
-            unsigned inc = c;
+            const unsigned cn = __popc(m[it]);
+            unsigned inc = cn;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const unsigned v = __shfl_up_sync(0xffffffffu, inc, d);
                 if (lane >= d) inc += v;
             }
             const unsigned total = __shfl_sync(0xffffffffu, inc, 31);
-            u64 g = g0 + (inc - c);
+            const unsigned off0 = (unsigned)(it * 512 + lane * 16);   // byte offset of this lane's group inside the tile
             unsigned mm = m[it];
-            const u64 base = (tile * NL_GROUPS + it * 32 + lane) * 16;
+            if (total > (unsigned)LI_BURST) {
+                // pathological text (a newline every few bytes): drain the queue, then let every lane walk its own bits
+                __syncwarp();
+                for (unsigned i = lane; i < qn; i += 32) bad += line_index_one(c, tile_byte0 + q[i], gq + i);
+                gq += qn;
+                qn = 0;
+                u64 g = gq + (inc - cn);
+                while (mm) {
+                    const int b = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    bad += line_index_one(c, tile_byte0 + off0 + b, g++);
+                }
+                gq += total;
+                __syncwarp();
+                continue;
+            }
+            unsigned slot = qn + (inc - cn);
             while (mm) {
                 const int b = __ffs(mm) - 1;
                 mm &= mm - 1;
-                const u64 pos = base + b;
-                if (((unsigned)g & lmask) == 1u) {
-                    const u64 r = g >> lshift;
-                    if (r < n_rec) seq_end[r] = (u32)pos;
-                }
-                const u64 g1 = g + 1;
-                const unsigned ph = (unsigned)g1 & lmask;
-                if (ph == 1u) {
-                    const u64 r = g1 >> lshift;
-                    if (r < n_rec) seq_start[r] = (u32)(pos + 1);
-                } else if (pos + 1 < nbytes) {
-                    if (ph == 0u) { if ((g1 >> lshift) < n_rec && bytes[pos + 1] != hdr) bad++; }
-                    else if (ph == 2u && bytes[pos + 1] != '+') bad++;     // only reached for FASTQ (lmask == 3)
-                }
-                g = g1;
+                q[slot++] = off0 + b;
             }
-            g0 += total;
+            qn += total;
+            if (qn > (unsigned)(LI_QUEUE - LI_BURST) || it == NL_ITERS - 1) {
+                __syncwarp();
+                for (unsigned i = lane; i < qn; i += 32) bad += line_index_one(c, tile_byte0 + q[i], gq + i);
+                gq += qn;
+                qn = 0;
+                __syncwarp();
+            }
         }
     }
     if (bad) atomicAdd(&counters[C_BADFMT], (u64)bad);

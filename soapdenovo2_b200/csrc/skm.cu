@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply(Table<NW> tab, 
     __shared__ const u64* s_ptr[SKM_MAX_SEGS];
     __shared__ u32 s_cum[SKM_MAX_SEGS + 1];
     __shared__ u32 s_warp[WARPS];
-    __shared__ u32 s_count, s_defer;
+    __shared__ u32 s_count, s_defer, s_batch;
     __shared__ unsigned s_new, s_tot_new, s_tot_spill;
     SmemTable<NW> st{s_dyn, s_dyn + NW * SKM_SLOTS, s_dyn + (NW + 1) * SKM_SLOTS, reinterpret_cast<unsigned short*>(s_dyn + (NW + 2) * SKM_SLOTS), &s_count};
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply(Table<NW> tab, 
         __syncthreads();   // previous bucket fully flushed (and the empty table visible on the first trip)
         const u32 cnt = ncnt;
         if (my_so) s_ptr[tid] = my_recs + (u64)nlo * RW;
-        if (tid == 0) { s_count = 0; s_new = 0; }
+        if (tid == 0) { s_count = 0; s_new = 0; s_batch = WARPS; }
         if (pos + gridDim.x < a.n_list && my_so) {
             const u32 nb = a.bucket_list ? a.bucket_list[pos + gridDim.x] : pos + gridDim.x;
             nlo = my_so[nb];
@@ -454,13 +454,25 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply(Table<NW> tab, 
                 for (int i = 0; i < NW + 1; i++) nx[i] = w[1 + i];
             }
         };
+        // batches are handed out dynamically (the first WARPS ones are pre-assigned): a warp that draws short runs takes more of them,
+        // so the warps reach the barrier before the flush together
         load_rec((u32)wid * 32u + lane);
-        for (u32 rb = (u32)wid * 32u; rb < R; rb += WARPS * 32) {
+        u32 nb = 0x7FFFFFFu;                                  // (a warp without a first batch must not draw one; x 32 still fits)
+        if ((u32)wid * 32u < R) {
+            if (lane == 0) nb = atomicAdd(&s_batch, 1u);
+            nb = __shfl_sync(0xffffffffu, nb, 0);
+        }
+        for (u32 rb = (u32)wid * 32u; rb < R;) {
             const u64 hdr = nh;
             u64 x[NW + 1];
 #pragma unroll
             for (int i = 0; i < NW + 1; i++) x[i] = nx[i];
-            load_rec(rb + WARPS * 32 + lane);                 // the next batch is in flight while this one is processed
+            const u32 rb_next = nb * 32u;
+            load_rec(rb_next + lane);                         // the next batch is in flight while this one is processed
+            if (rb_next < R) {
+                if (lane == 0) nb = atomicAdd(&s_batch, 1u);
+                nb = __shfl_sync(0xffffffffu, nb, 0);
+            }
             const bool valid = rb + lane < R;
             const u32 n = valid ? (u32)skm_rec_n(hdr) : 0u;
             u32 inc = n;
@@ -499,6 +511,7 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply(Table<NW> tab, 
                 }
                 __syncwarp();
             }
+            rb = rb_next;
         }
         __syncthreads();
         // ---- flush: one global update per distinct k-mer of the bucket, walking the claim list (every thread busy)

@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(256) k_thin_walk(Table<NW> tab, KParams<NW> kp
         r.n1_slot = s1; r.out_slot = w.out_slot;
         r.code = w.sm ? w.ch : (4u | (w.ch ^ 2u));   // dislink2prevUncertain: smaller ? l[ch] : r[ch^2]
         r.state = w.status == 1 ? 0u : 1u;            // too long -> nothing to do
+        if (w.status != 1) r.code |= 32u;             // no `out` node: out_slot is meaningless (k_thin_unmark must not follow it)
         if (w.status < 0) atomicAdd(err, 1ull);
         rec[i] = r;
     }
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(256) k_thin_commit(Table<NW> tab, const u64* c
 template <int NW>
 __global__ void __launch_bounds__(256) k_thin_unmark(Table<NW> tab, const u64* cand, u64 n, const TipRec* rec, u64* mark) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        if (rec[i].code & 32u) continue;   // never marked anything (its out_slot is 0: following it reads slot 0's aux, ~0 when that slot is empty)
         mark[tab.slots[rec[i].out_slot].aux] = EMPTY64;
         mark[cand[i]] = EMPTY64;
     }
