@@ -194,12 +194,14 @@ __global__ void __launch_bounds__(SKM_PART_THREADS) k_skm_rescan(SkmSendArgs a, 
 // A thread that meets a BUSY key0 whose other bits match waits for the publication (independent thread scheduling: the claimer makes
 // progress even inside the same warp).  The claimer also appends the slot to the claim list (the flush walks the list, not the
 // table) and prefetches the k-mer's home slot in the GLOBAL table into L2, so that the flush finds it there.
-template <int NW>
+// S slots (any size: the slot index is a multiply-shift range reduction of a 32-bit hash), claims stop at LIMIT so that the
+// table can never fill up completely whatever the number of concurrent claimers; LT = type of the claim-list entries.
+template <int NW, int S, int LIMIT, class LT>
 struct SmemTable {
     u64* key;   // [NW * S]
     u64* pay;
     u64* rnk;
-    unsigned short* list;
+    LT* list;
     u32* count;
     // Two phases with a warp barrier between them (the caller's __syncwarp over the lanes that have an instance): first every lane
     // finds or claims its slot (lanes differ only in the number of probes), then the lanes that found an existing key apply their
@@ -207,24 +209,24 @@ struct SmemTable {
     // others keep probing: the update code then executes several times per step with a few active lanes each).
     // find(): 1 = key present at idx, 2 = claimed by this lane (first instance already recorded), 3 = no room (caller spills)
     __device__ __forceinline__ int find(const Table<NW>& tab, const Kmer<NW>& k, unsigned left, unsigned right, u64 rank, u32& idx) const {
-        idx = skm_slot_hash(k, SKM_LOG2_SLOTS);
+        idx = (u32)(((u64)skm_slot_hash(k, 32) * (u64)S) >> 32);
         volatile u64* vkey = key;
         volatile u64* vpay = pay;
         volatile u64* vrnk = rnk;
-        for (int probe = 0; probe < SKM_SLOTS; probe++) {
+        for (int probe = 0; probe < S; probe++) {
             u64 k0 = vkey[idx];
             if (k0 == EMPTY64) {
-                if (*(volatile u32*)count >= (u32)SKM_SOFT_LIMIT) return 3;
+                if (*(volatile u32*)count >= (u32)LIMIT) return 3;
                 u64 old = atomicCAS(&key[idx], EMPTY64, k.w[0] | BUSY_BIT);
                 if (old == EMPTY64) {
 #pragma unroll
-                    for (int w = 1; w < NW; w++) vkey[w * SKM_SLOTS + idx] = k.w[w];
+                    for (int w = 1; w < NW; w++) vkey[w * S + idx] = k.w[w];
                     vpay[idx] = payload_apply(PAYLOAD_FRESH, left, right);
                     vrnk[idx] = rank;
                     __threadfence_block();
                     vkey[idx] = k.w[0];
                     const u32 n = atomicAdd(count, 1u);
-                    list[n] = (unsigned short)idx;
+                    list[n] = (LT)idx;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(tab.slots + (table_hash(k) & tab.mask)));
                     return 2;
                 }
@@ -234,10 +236,10 @@ struct SmemTable {
                 while (k0 & BUSY_BIT) k0 = vkey[idx];
                 bool same = true;
 #pragma unroll
-                for (int w = 1; w < NW; w++) same = same && vkey[w * SKM_SLOTS + idx] == k.w[w];
+                for (int w = 1; w < NW; w++) same = same && vkey[w * S + idx] == k.w[w];
                 if (same) return 1;
             }
-            idx = (idx + 1) & (SKM_SLOTS - 1);
+            idx = idx + 1 == (u32)S ? 0u : idx + 1;
         }
         return 3;
     }
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply(Table<NW> tab, 
     __shared__ u32 s_warp[WARPS];
     __shared__ u32 s_count, s_defer, s_batch;
     __shared__ unsigned s_new, s_tot_new, s_tot_spill;
-    SmemTable<NW> st{s_dyn, s_dyn + NW * SKM_SLOTS, s_dyn + (NW + 1) * SKM_SLOTS, reinterpret_cast<unsigned short*>(s_dyn + (NW + 2) * SKM_SLOTS), &s_count};
+    SmemTable<NW, SKM_SLOTS, SKM_SOFT_LIMIT, unsigned short> st{s_dyn, s_dyn + NW * SKM_SLOTS, s_dyn + (NW + 1) * SKM_SLOTS, reinterpret_cast<unsigned short*>(s_dyn + (NW + 2) * SKM_SLOTS), &s_count};
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned lane_le = 0xffffffffu >> (31 - lane);
     for (int i = tid; i < SKM_SLOTS; i += SKM_APPLY_THREADS) st.key[i] = EMPTY64;   // the flush re-empties what it merges
@@ -540,6 +542,193 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply(Table<NW> tab, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ aggregation, one WARP per bucket
+// Same work as k_skm_apply with the bucket sized for one warp (about 100 distinct k-mers: 8x more buckets) and a private
+// shared-memory table per warp.  Nothing in it is CTA-wide: no barrier, no waiting for the slowest warp of a bucket, and the fixed
+// cost of a bucket (segment ranges, table room, flush round trips) is paid by one warp while the other warps of the SM compute.
+template <int NW>
+struct SkmWarpGeom {
+    static constexpr int SLOTS = NW == 2 ? 200 : 110;
+    static constexpr int LIMIT = SLOTS - 40;              // 32 lanes claim concurrently
+    static constexpr int BYTES = ((NW + 2) * SLOTS * 8 + SLOTS + 32 * 12 + 16 + 15) & ~15;   // table, u8 claim list, 32 dense segment entries, count
+};
+template <int NW>
+__global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply_w(Table<NW> tab, KParams<NW> kp, SkmApplyArgs a) {
+    constexpr int RW = NW + 2, WARPS = SKM_APPLY_THREADS / 32, S = SkmWarpGeom<NW>::SLOTS;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned char* mine = s_raw + (size_t)wid * SkmWarpGeom<NW>::BYTES;
+    u64* tkey = reinterpret_cast<u64*>(mine);
+    u64* tpay = tkey + NW * S;
+    u64* trnk = tpay + S;
+    const u64** d_ptr = reinterpret_cast<const u64**>(trnk + S);          // [32] dense segment entries: first record of the range
+    u32* d_pe = reinterpret_cast<u32*>(d_ptr + 32);                        // [32] its first record index inside the group
+    u32* t_count = d_pe + 32;
+    unsigned char* tlist = reinterpret_cast<unsigned char*>(t_count + 4);
+    SmemTable<NW, S, SkmWarpGeom<NW>::LIMIT, unsigned char> st{tkey, tpay, trnk, tlist, t_count};
+    const unsigned lane_le = 0xffffffffu >> (31 - lane);
+    for (int i = lane; i < S; i += 32) tkey[i] = EMPTY64;   // the flush re-empties what it merges
+    __syncwarp();
+    const int n_segs = (int)a.segs->n;
+    unsigned tot_new = 0, tot_spill = 0;
+    u64 credit = 0;                      // lane 0: table room this warp holds
+    const u32 n_warps = gridDim.x * WARPS;
+    for (u32 pos = blockIdx.x * WARPS + wid; pos < a.n_list; pos += n_warps) {
+        const u32 b = a.bucket_list ? a.bucket_list[pos] : pos;
+        // ---- records of the bucket (all segments) -> table room
+        u32 R = 0;
+        for (int sg = 0; sg < n_segs; sg += 32) {
+            const int j = sg + lane;
+            u32 c = 0;
+            if (j < n_segs) { const u32* so = a.segs->segoff[j]; c = so[b + 1] - so[b]; }
+            R += __reduce_add_sync(0xffffffffu, c);
+        }
+        if (R == 0) continue;
+        int defer = 0;
+        if (lane == 0) {
+            const u64 bound = (u64)R * SKM_MAX_RUN;
+            if (credit < bound) {
+                unsigned long long* res = (unsigned long long*)&a.counters[C_RESERVED];
+                const u64 want = bound - credit, ask = want > SKM_CREDIT ? want : SKM_CREDIT;
+                u64 old = atomicAdd(res, (unsigned long long)ask);
+                if (old + ask <= a.limit) credit += ask;
+                else {
+                    atomicAdd(res, (unsigned long long)(0ull - ask));
+                    bool got = false;
+                    if (ask != want) {
+                        old = atomicAdd(res, (unsigned long long)want);
+                        if (old + want <= a.limit) { credit += want; got = true; }
+                        else atomicAdd(res, (unsigned long long)(0ull - want));
+                    }
+                    if (!got) {
+                        defer = 1;
+                        a.deferred[atomicAdd((unsigned long long*)&a.counters[C_DEFER], 1ull)] = b;
+                        atomicMax((unsigned long long*)&a.counters[C_MAXU], (unsigned long long)bound);
+                    }
+                }
+            }
+            if (!defer) credit -= bound;
+            *t_count = 0;
+        }
+        defer = __shfl_sync(0xffffffffu, defer, 0);
+        if (defer) continue;
+        unsigned my_new = 0;
+        for (int sg = 0; sg < n_segs; sg += 32) {
+            // the non-empty ranges of this group of segments, made dense: entry r = (first record pointer, first record index)
+            const int j = sg + lane;
+            u32 c = 0;
+            const u64* ptr = nullptr;
+            if (j < n_segs) {
+                const u32* so = a.segs->segoff[j];
+                const u32 lo = so[b];
+                c = so[b + 1] - lo;
+                ptr = a.segs->recs[j] + (u64)lo * RW;
+            }
+            u32 inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 v = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += v;
+            }
+            const u32 T = __shfl_sync(0xffffffffu, inc, 31);      // records in this group
+            if (T == 0) continue;
+            const unsigned nz = __ballot_sync(0xffffffffu, c > 0);
+            const int nv = __popc(nz);
+            __syncwarp();
+            if (c > 0) {
+                const int r = __popc(nz & (lane_le >> 1));
+                d_ptr[r] = ptr;
+                d_pe[r] = inc - c;
+            }
+            __syncwarp();
+            const u32 my_pe = lane < nv ? d_pe[lane] : 0xFFFFFFFFu;
+            for (u32 rb = 0; rb < T; rb += 32) {
+                // ---- 32 consecutive records of the group, one per lane
+                const u32 q = rb + lane;
+                const bool valid = q < T;
+                u64 hdr = 0, x[NW + 1];
+#pragma unroll
+                for (int i = 0; i < NW + 1; i++) x[i] = 0;
+                {
+                    const unsigned starts = __reduce_or_sync(0xffffffffu, (lane < nv && my_pe > rb && my_pe - rb < 32u) ? 1u << (my_pe - rb) : 0u);
+                    const int first = __popc(__ballot_sync(0xffffffffu, lane < nv && my_pe <= rb)) - 1;
+                    if (valid) {
+                        const int src = first + __popc(starts & lane_le);
+                        const uint4* p = reinterpret_cast<const uint4*>(d_ptr[src] + (u64)(q - d_pe[src]) * RW);
+                        u64 w[RW];
+#pragma unroll
+                        for (int i = 0; i < RW / 2; i++) {
+                            const uint4 v = __ldg(p + i);
+                            w[2 * i] = (u64)v.x | ((u64)v.y << 32);
+                            w[2 * i + 1] = (u64)v.z | ((u64)v.w << 32);
+                        }
+                        hdr = w[0];
+#pragma unroll
+                        for (int i = 0; i < NW + 1; i++) x[i] = w[1 + i];
+                    }
+                }
+                const u32 n = valid ? (u32)skm_rec_n(hdr) : 0u;
+                u32 ic = n;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const u32 v = __shfl_up_sync(0xffffffffu, ic, d);
+                    if (lane >= d) ic += v;
+                }
+                const u32 I = __shfl_sync(0xffffffffu, ic, 31);
+                const u32 pe = ic - n;
+                for (u32 q0 = 0; q0 < I; q0 += 32) {
+                    const u32 qi = q0 + lane;
+                    const bool has = qi < I;
+                    const unsigned starts = __reduce_or_sync(0xffffffffu, (valid && pe > q0 && pe - q0 < 32u) ? 1u << (pe - q0) : 0u);
+                    const int first = __popc(__ballot_sync(0xffffffffu, valid && pe <= q0)) - 1;
+                    const int src = (first + __popc(starts & lane_le)) & 31;
+                    const int t = (int)(qi - __shfl_sync(0xffffffffu, pe, src));
+                    const u64 h = shfl64(hdr, src);
+                    u64 y[NW + 1];
+#pragma unroll
+                    for (int i = 0; i < NW + 1; i++) y[i] = shfl64(x[i], src);
+                    const unsigned has_mask = __ballot_sync(0xffffffffu, has);
+                    if (has) {
+                        const SkmInst<NW> in = skm_instance_rec<NW>(kp, h, y, t);
+                        const u64 rank = skm_rec_rank(h, t);
+                        u32 slot;
+                        const int state = st.find(tab, in.canon, in.left, in.right, rank, slot);
+                        __syncwarp(has_mask);
+                        if (state == 1) st.apply(slot, in.left, in.right, rank);
+                        else if (state == 3) {
+                            my_new += table_insert(tab, in.canon, in.left, in.right, rank);
+                            tot_spill++;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            __syncwarp();   // d_ptr / d_pe are rewritten by the next group
+        }
+        // ---- flush
+        const u32 n_claimed = *(volatile u32*)t_count;
+        for (u32 i = lane; i < n_claimed; i += 32) {
+            const u32 idx = tlist[i];
+            Kmer<NW> k;
+#pragma unroll
+            for (int w = 0; w < NW; w++) k.w[w] = tkey[w * S + idx];
+            my_new += table_merge(tab, k, tpay[idx], trnk[idx]);
+            tkey[idx] = EMPTY64;
+        }
+        const unsigned bucket_new = __reduce_add_sync(0xffffffffu, my_new);
+        tot_new += my_new;
+        if (lane == 0) credit += (u64)R * SKM_MAX_RUN - (u64)bucket_new;
+        __syncwarp();
+    }
+    if (lane == 0 && credit) atomicAdd((unsigned long long*)&a.counters[C_RESERVED], (unsigned long long)(0ull - credit));
+    tot_new = __reduce_add_sync(0xffffffffu, tot_new);
+    tot_spill = __reduce_add_sync(0xffffffffu, tot_spill);
+    if (lane == 0) {
+        if (tot_new) atomicAdd(&a.counters[C_DISTINCT], (u64)tot_new);
+        if (tot_spill) atomicAdd(&a.counters[C_MISC2], (u64)tot_spill);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 template <int NW>
 static constexpr size_t skm_apply_smem() {
@@ -555,12 +744,15 @@ void EngineT<NW>::skm_init() {
     u64 est = 0;   // expected number of distinct k-mers on THIS GPU
     if (prm_.table_slots) est = prm_.table_slots / 2;
     else if (prm_.initG) est = (u64)((double)prm_.P * (double)ref_static_set_size(prm_.initG, prm_.P, prm_.flavour127 != 0) * 0.77) / world;
-    u64 Bo = est ? next_pow2_u64((est + SKM_SLOTS / 2 - 1) / (SKM_SLOTS / 2)) : (1ull << 16);
+    if (const char* e = getenv("PGB200_SKM_WARP")) skm_warp_mode_ = atoi(e);
+    // distinct k-mers a bucket should hold on average: half a CTA table, or 45 % of a warp table
+    const u64 per_bucket = skm_warp_mode_ ? (u64)(SkmWarpGeom<NW>::SLOTS * 45 / 100) : (u64)(SKM_SLOTS / 2);
+    u64 Bo = est ? next_pow2_u64((est + per_bucket - 1) / per_bucket) : (skm_warp_mode_ ? 1ull << 19 : 1ull << 16);
     if (Bo < 1024) Bo = 1024;
     u64 B = Bo * world;
     if (const char* e = getenv("PGB200_SKM_BUCKETS")) B = strtoull(e, nullptr, 0);
     if (B < (u64)world) B = world;
-    if (B > (1ull << SKM_MAX_BUCKET_BITS)) B = 1ull << SKM_MAX_BUCKET_BITS;   // the side buffer packs the bucket in 24 bits
+    if (B > (1ull << SKM_MAX_BUCKET_BITS)) B = 1ull << SKM_MAX_BUCKET_BITS;   // the side buffer packs the bucket in 26 bits
     skm_geom_ = make_skm_geom(prm_.K, (u32)B);
     skm_own_lo_ = skm_owner_lo((u32)B, world, prm_.rank);
     skm_own_hi_ = prm_.rank + 1 < world ? skm_owner_lo((u32)B, world, prm_.rank + 1) : (u32)B;
@@ -586,6 +778,7 @@ void EngineT<NW>::skm_init() {
         PG_CUDA(cudaFuncSetAttribute(k_skm_rescan<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
     }
     PG_CUDA(cudaFuncSetAttribute(k_skm_apply<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skm_apply_smem<NW>()));
+    PG_CUDA(cudaFuncSetAttribute(k_skm_apply_w<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((SKM_APPLY_THREADS / 32) * SkmWarpGeom<NW>::BYTES)));
     if (prm_.verbose) fprintf(stderr, "[pgb200] aggregated pass 1: %u buckets (%u owned by GPU %d of %d), minimizer length %d, window %d\n", skm_geom_.n_buckets,
                               skm_own_hi_ - skm_own_lo_, prm_.rank, world, skm_geom_.m, skm_geom_.w);
 }
@@ -822,8 +1015,15 @@ void EngineT<NW>::skm_launch_apply(const u32* list, u32 n_list, u32* deferred_ou
     aa.segs = segs; aa.bucket_list = list; aa.n_list = n_list; aa.counters = d_cnt_;
     aa.limit = (u64)(0.85 * (double)cap_);
     aa.deferred = deferred_out;
-    const unsigned blocks = (unsigned)std::min<u64>((u64)n_list, 148ull * (NW == 2 ? 3 : 2));
-    if (blocks) k_skm_apply<NW><<<blocks, SKM_APPLY_THREADS, skm_apply_smem<NW>(), st_>>>(tab_, kp_, aa);
+    if (skm_warp_mode_) {
+        const size_t smem = (size_t)(SKM_APPLY_THREADS / 32) * SkmWarpGeom<NW>::BYTES;
+        const unsigned per_sm = (unsigned)std::min<size_t>((227 * 1024) / (smem + 1024), 2048 / SKM_APPLY_THREADS);
+        const unsigned blocks = (unsigned)std::min<u64>(((u64)n_list + SKM_APPLY_THREADS / 32 - 1) / (SKM_APPLY_THREADS / 32), 148ull * per_sm);
+        if (blocks) k_skm_apply_w<NW><<<blocks, SKM_APPLY_THREADS, smem, st_>>>(tab_, kp_, aa);
+    } else {
+        const unsigned blocks = (unsigned)std::min<u64>((u64)n_list, 148ull * (NW == 2 ? 3 : 2));
+        if (blocks) k_skm_apply<NW><<<blocks, SKM_APPLY_THREADS, skm_apply_smem<NW>(), st_>>>(tab_, kp_, aa);
+    }
     PG_CUDA(cudaGetLastError());
     PG_CUDA(cudaMemcpyAsync(h_flush_, d_cnt_ + C_XERR, 5 * sizeof(u64), cudaMemcpyDeviceToHost, st_));   // XERR, XUSED, RESERVED, DEFER, MAXU
     p1_.launches += 2;

@@ -23,7 +23,7 @@ namespace pgb {
 
 constexpr int SKM_MAX_RUN = 32;      // k-mers per record: 1 + n + K bases must fit NW+1 words (96 bases at K=63, 160 at K=127)
 constexpr int SKM_MAX_M = 15;        // minimizer length (2m bits must fit in 32)
-constexpr int SKM_MAX_BUCKET_BITS = 24;
+constexpr int SKM_MAX_BUCKET_BITS = 26;
 constexpr int SKM_MAX_SEGS = 128;    // segments (fed chunks, over all senders) one aggregation launch can read
 
 struct SkmGeom {
@@ -64,11 +64,11 @@ PG_HD int skm_owner_of(u32 n_buckets, int world, u32 b) {
     return o;
 }
 
-// side-buffer entry of one run (written by the counting pass, consumed by the scatter pass): bucket | (n - 1) << 24 | last << 29
-PG_HD u32 skm_side_pack(u32 b, int n, bool last) { return b | ((u32)(n - 1) << SKM_MAX_BUCKET_BITS) | (last ? 1u << 29 : 0u); }
+// side-buffer entry of one run (written by the counting pass, consumed by the scatter pass): bucket (26 bits) | (n - 1) << 26 | last << 31
+PG_HD u32 skm_side_pack(u32 b, int n, bool last) { return b | ((u32)(n - 1) << SKM_MAX_BUCKET_BITS) | (last ? 1u << 31 : 0u); }
 PG_HD u32 skm_side_bucket(u32 e) { return e & ((1u << SKM_MAX_BUCKET_BITS) - 1u); }
 PG_HD int skm_side_n(u32 e) { return (int)((e >> SKM_MAX_BUCKET_BITS) & 31u) + 1; }
-PG_HD bool skm_side_last(u32 e) { return ((e >> 29) & 1u) != 0; }
+PG_HD bool skm_side_last(u32 e) { return (e >> 31) != 0; }
 
 // Split one read into runs.  scratch[slot * stride] (slot < 2 * g.w) holds, per thread, the order values of the current block of w
 // m-mer positions and the suffix minima of the previous block: the minimum of a window of w positions is

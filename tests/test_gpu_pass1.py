@@ -15,14 +15,16 @@ def _build():
     util.build_oracle()
 
 
-@pytest.fixture(params=["direct", "aggregated"], autouse=True)
+@pytest.fixture(params=["direct", "aggregated", "aggregated_warp"], autouse=True)
 def _insert_mode(request, monkeypatch):
-    """Every case runs twice: per-instance inserts (k_chop_insert, PGB200_SKM=0) and the default aggregated pass 1 (super-k-mer
-    records, skm.cu)."""
+    """Every case runs three times: per-instance inserts (k_chop_insert, PGB200_SKM=0), the default aggregated pass 1 (super-k-mer
+    records, one CTA per bucket, skm.cu) and its one-warp-per-bucket variant (PGB200_SKM_WARP=1)."""
+    monkeypatch.delenv("PGB200_SKM", raising=False)
+    monkeypatch.delenv("PGB200_SKM_WARP", raising=False)
     if request.param == "direct":
         monkeypatch.setenv("PGB200_SKM", "0")
-    else:
-        monkeypatch.delenv("PGB200_SKM", raising=False)
+    elif request.param == "aggregated_warp":
+        monkeypatch.setenv("PGB200_SKM_WARP", "1")
 
 
 def _feed_cfg_files(eng, files, fastq, stride=1, base=0, **kw):
@@ -125,7 +127,8 @@ def test_aggregated_stress_paths(tmp_path, monkeypatch, K, flav, buckets, arena_
     """The aggregated pass 1 under stress: 1..4 buckets (every k-mer spills past the shared-memory table and buckets are deferred
     until the tiny global table has grown), a 1 MB arena (mid-stream flushes because the arena is full), periodic flushes, many
     small chunks.  Same table dump as the oracle."""
-    monkeypatch.delenv("PGB200_SKM", raising=False)
+    if os.environ.get("PGB200_SKM") == "0":
+        pytest.skip("aggregated paths only")
     if buckets != "0":
         monkeypatch.setenv("PGB200_SKM_BUCKETS", buckets)
     if arena_mb != "0":
