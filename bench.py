@@ -222,7 +222,7 @@ def reference_arm(args, torch, workdir, workload):
     count; --steps / --warmup apply to the GPU arm only (a run takes minutes)."""
     cfg, n_pairs = write_read_files(torch, workdir, args.genome, args.coverage, 42, "refarm")
     init_g = max(2, int(args.genome * 2.3 * 24 * 1.4 / (1 << 30)) + 1)   # -a: static tables large enough (prlHashReads.c:372-385)
-    runs, budget, t_start = [], float(os.environ.get("PGB200_REF_BUDGET_S", "420")), time.perf_counter()
+    runs, budget, t_start = [], float(os.environ.get("PGB200_REF_BUDGET_S", "300")), time.perf_counter()
     for thr in thread_choices():
         if runs and time.perf_counter() - t_start + runs[-1]["seconds"] > budget:
             break
@@ -327,8 +327,10 @@ def main():
     total_instances = 2 * n_pairs * (world if weak else 1) * (RD_LEN - K + 1)
     xchg = None
     if world > 1:
-        # arena: this rank's share of the job's records (about one record per 14 k-mers; 2.5x head room), double-buffered inside
-        xchg = pdist.RecordExchange(eng, dist, cap_records=int(2.5 * total_instances / 14 / world) + (1 << 20))
+        # arena: this rank's share of the job's records (about one record per 15.9 k-mers at K=63, 10 at K=127; 40 % head room),
+        # double-buffered inside the engine
+        per_rec = 15.0 if K <= 63 else 9.0
+        xchg = pdist.RecordExchange(eng, dist, cap_records=int(float(os.environ.get("PGB200_BENCH_ARENA_FACTOR", "1.4")) * total_instances / per_rec / world) + (1 << 20))
 
     def one_step(bufs, on_device):
         """bufs: per mate a device tensor, or {work index: (host pointer, nbytes)} for this rank's chunks."""
@@ -478,7 +480,7 @@ def main():
                                    f"owner GPU's arena by the partition kernel (NVLink peer stores over CUDA IPC mappings, no library collective on the data path); one barrier per step"
                                    if world > 1 else "1 GPU"),
                    "insert_mode": "aggregated pass 1 (super-k-mer records, one table update per distinct k-mer) for value AND e2e" if os.environ.get("PGB200_SKM", "1") != "0" else "PGB200_SKM=0: per-instance inserts",
-                   "parity": parity,
+                   "parity": parity, "digest": digest,
                    "l2_policy": f"inputs ({(t1.numel()+t2.numel())/1e9:.1f} GB text per rank, {st.table_slots*32*(2 if K>63 else 1)/1e9:.1f} GB table) are far larger than the 126 MB L2; the table is cleared every step"},
         "e2e": e2e, "gpu_launches": int(r["launches"]), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_b}))
 

@@ -336,6 +336,7 @@ struct SkmApplyArgs {
     u32* deferred;
 };
 constexpr u64 SKM_CREDIT = 1ull << 16;   // table room a CTA reserves at a time (keys)
+constexpr u64 SKM_CREDIT_W = 1ull << 12; // ... and a warp of the one-warp-per-bucket kernel (there are 10x more of them)
 
 __device__ __forceinline__ u64 shfl64(u64 v, int src) { return (u64)__shfl_sync(0xffffffffu, (unsigned long long)v, src); }
 
@@ -589,7 +590,7 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply_w(Table<NW> tab
             const u64 bound = (u64)R * SKM_MAX_RUN;
             if (credit < bound) {
                 unsigned long long* res = (unsigned long long*)&a.counters[C_RESERVED];
-                const u64 want = bound - credit, ask = want > SKM_CREDIT ? want : SKM_CREDIT;
+                const u64 want = bound - credit, ask = want > SKM_CREDIT_W ? want : SKM_CREDIT_W;
                 u64 old = atomicAdd(res, (unsigned long long)ask);
                 if (old + ask <= a.limit) credit += ask;
                 else {

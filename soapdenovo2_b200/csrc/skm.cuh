@@ -42,10 +42,11 @@ inline SkmGeom make_skm_geom(int K, u32 n_buckets) {
     return g;
 }
 
-// bijective 32-bit mixer (murmur3 finaliser): equal order values <=> equal canonical m-mers, so ties cannot split a k-mer
-// and its reverse complement over two buckets
+// Order value of a canonical m-mer: a bijective 32-bit mixer (odd multiply, xor-shift, odd multiply).  The bucket of a k-mer is a
+// function of the MINIMUM order value over its m-mers -- the same multiset on both strands -- so a k-mer and its reverse complement
+// always agree on it; the mixer only has to make the minimum look random with respect to the sequence.
 PG_HD u32 skm_fmix32(u32 x) {
-    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x85EBCA6Bu;
     return x;
 }
 PG_HD u32 skm_order(u32 fm, u32 rm) { return skm_fmix32(fm < rm ? fm : rm); }
@@ -85,24 +86,28 @@ PG_HD void skm_scan_read(const SkmGeom& g, const u64* wp, int L, u32* scratch, i
     u32* suf_blk = scratch + w * stride;    // suffix minima of the previous block
     u32 fm = 0, rm = 0, pref = 0xFFFFFFFFu;
     int o = 0;                              // offset of m-mer position p inside its block
+    u32* cur_p = cur_blk;                   // = cur_blk + o * stride
+    const u32* suf_p = suf_blk + stride;    // = suf_blk + (o + 1) * stride
     u32 cur_b = 0, cur_min = 0;
     bool have_min = false;
     int run_start = 0, run_len = 0;
-    u64 cur = wp[0];
+    const int rsh = 2 * (m - 1);
+    u64 cur = 0;
     for (int i = 0; i < L; i++) {
-        if (i && (i & 31) == 0) cur = wp[i >> 5];
-        const u32 c = (u32)((cur >> (2 * (i & 31))) & 3);
+        if ((i & 31) == 0) cur = wp[i >> 5];
+        const u32 c = (u32)cur & 3u;
+        cur >>= 2;
         fm = ((fm << 2) | c) & g.mmask;
-        rm = (rm >> 2) | ((c ^ 2u) << (2 * (m - 1)));
+        rm = (rm >> 2) | ((c ^ 2u) << rsh);
         if (i < m - 1) continue;
         const u32 ov = skm_order(fm, rm);
-        cur_blk[o * stride] = ov;
+        *cur_p = ov;
         pref = ov < pref ? ov : pref;
         const int j = i - K + 1;            // k-mer position; its m-mers are the positions p-w+1 .. p
         if (j >= 0) {
             u32 minval = pref;
             if (o != w - 1) {
-                const u32 sv = suf_blk[(o + 1) * stride];
+                const u32 sv = *suf_p;
                 minval = sv < minval ? sv : minval;
             }
             bool cut = run_len == SKM_MAX_RUN;
@@ -120,14 +125,20 @@ PG_HD void skm_scan_read(const SkmGeom& g, const u64* wp, int L, u32* scratch, i
             if (run_len == 0) run_start = j;
             run_len++;
         }
+        cur_p += stride;
+        suf_p += stride;
         if (++o == w) {                     // block complete: its suffix minima serve the next w-1 windows
             u32 run = 0xFFFFFFFFu;
-            for (int q = w - 1; q >= 0; q--) {
-                const u32 v = cur_blk[q * stride];
+            const u32* src = cur_blk + (w - 1) * stride;
+            u32* dst = suf_blk + (w - 1) * stride;
+            for (int q = w - 1; q >= 0; q--, src -= stride, dst -= stride) {
+                const u32 v = *src;
                 run = v < run ? v : run;
-                suf_blk[q * stride] = run;
+                *dst = run;
             }
             o = 0;
+            cur_p = cur_blk;
+            suf_p = suf_blk + stride;
             pref = 0xFFFFFFFFu;
         }
     }

@@ -41,6 +41,7 @@ def test_configs1_full_size_properties():
     G, K = 100_000_000, 63
     n_pairs = int(G * 30 / 300)
     t1, t2 = bench.gen_pe_fastq_gpu(torch, torch.device("cuda", 0), G, n_pairs, seed=42)
+    torch.cuda.synchronize()   # the engine's streams are non-blocking: they do not wait for torch's stream by themselves
     eng = api.PregraphEngine(K=K, P=8, max_rd_len=150, table_slots=1 << 29)
     st, hist, lin = _feed_all(eng, torch, t1, t2, bench, 1_000_000)
     assert st.records == 2 * n_pairs and st.reads_kept == 2 * n_pairs
@@ -74,6 +75,7 @@ def test_strand_symmetry_10mbp():
 
     dumps = []
     for a, b in ((t1, t2), (revcomp_text(t1), revcomp_text(t2))):
+        torch.cuda.synchronize()
         eng = api.PregraphEngine(K=K, P=4, initG=4, max_rd_len=150)
         st, hist, lin = _feed_all(eng, torch, a, b, bench, 1_000_000)
         eng.build_layout()
