@@ -567,6 +567,9 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply_w(Table<NW> tab
     u32* t_count = d_pe + 32;
     unsigned char* tlist = reinterpret_cast<unsigned char*>(t_count + 4);
     SmemTable<NW, S, SkmWarpGeom<NW>::LIMIT, unsigned char> st{tkey, tpay, trnk, tlist, t_count};
+    volatile u64* vkey = tkey;
+    volatile u64* vpay = tpay;
+    volatile u64* vrnk = trnk;
     const unsigned lane_le = 0xffffffffu >> (31 - lane);
     for (int i = lane; i < S; i += 32) tkey[i] = EMPTY64;   // the flush re-empties what it merges
     __syncwarp();
@@ -577,11 +580,17 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply_w(Table<NW> tab
     for (u32 pos = blockIdx.x * WARPS + wid; pos < a.n_list; pos += n_warps) {
         const u32 b = a.bucket_list ? a.bucket_list[pos] : pos;
         // ---- records of the bucket (all segments) -> table room
-        u32 R = 0;
+        u32 R = 0, c0 = 0;                 // c0 / ptr0: this lane's range in the first group of 32 segments (kept for the second pass)
+        const u64* ptr0 = nullptr;
         for (int sg = 0; sg < n_segs; sg += 32) {
             const int j = sg + lane;
             u32 c = 0;
-            if (j < n_segs) { const u32* so = a.segs->segoff[j]; c = so[b + 1] - so[b]; }
+            if (j < n_segs) {
+                const u32* so = a.segs->segoff[j];
+                const u32 lo = so[b];
+                c = so[b + 1] - lo;
+                if (sg == 0) { c0 = c; ptr0 = a.segs->recs[j] + (u64)lo * RW; }
+            }
             R += __reduce_add_sync(0xffffffffu, c);
         }
         if (R == 0) continue;
@@ -617,13 +626,16 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply_w(Table<NW> tab
         for (int sg = 0; sg < n_segs; sg += 32) {
             // the non-empty ranges of this group of segments, made dense: entry r = (first record pointer, first record index)
             const int j = sg + lane;
-            u32 c = 0;
-            const u64* ptr = nullptr;
-            if (j < n_segs) {
-                const u32* so = a.segs->segoff[j];
-                const u32 lo = so[b];
-                c = so[b + 1] - lo;
-                ptr = a.segs->recs[j] + (u64)lo * RW;
+            u32 c = c0;
+            const u64* ptr = ptr0;
+            if (sg > 0) {
+                c = 0;
+                if (j < n_segs) {
+                    const u32* so = a.segs->segoff[j];
+                    const u32 lo = so[b];
+                    c = so[b + 1] - lo;
+                    ptr = a.segs->recs[j] + (u64)lo * RW;
+                }
             }
             u32 inc = c;
 #pragma unroll
@@ -688,18 +700,62 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply_w(Table<NW> tab
                     u64 y[NW + 1];
 #pragma unroll
                     for (int i = 0; i < NW + 1; i++) y[i] = shfl64(x[i], src);
-                    const unsigned has_mask = __ballot_sync(0xffffffffu, has);
+                    // ---- the warp owns this table: everything below is warp-synchronous (no BUSY protocol, no waiting on other warps)
+                    SkmInst<NW> in;
+                    u64 rank = 0;
+                    u32 idx = 0;
+                    int state = 5;                      // 0 searching | 1 key found at idx | 2 at an empty slot | 3 no room | 4 claimed | 5 no instance
                     if (has) {
-                        const SkmInst<NW> in = skm_instance_rec<NW>(kp, h, y, t);
-                        const u64 rank = skm_rec_rank(h, t);
-                        u32 slot;
-                        const int state = st.find(tab, in.canon, in.left, in.right, rank, slot);
-                        __syncwarp(has_mask);
-                        if (state == 1) st.apply(slot, in.left, in.right, rank);
-                        else if (state == 3) {
-                            my_new += table_insert(tab, in.canon, in.left, in.right, rank);
-                            tot_spill++;
+                        in = skm_instance_rec<NW>(kp, h, y, t);
+                        rank = skm_rec_rank(h, t);
+                        idx = (u32)(((u64)skm_slot_hash(in.canon, 32) * (u64)S) >> 32);
+                        state = 0;
+                    }
+                    for (;;) {
+                        // search: one probe per trip for every lane still looking; the lanes stay together
+                        while (__any_sync(0xffffffffu, state == 0)) {
+                            if (state == 0) {
+                                const u64 k0 = vkey[idx];
+                                if (k0 == EMPTY64) state = 2;
+                                else {
+                                    bool same = k0 == in.canon.w[0];
+#pragma unroll
+                                    for (int w = 1; w < NW; w++) same = same && vkey[w * S + idx] == in.canon.w[w];
+                                    if (same) state = 1;
+                                    else idx = idx + 1 == (u32)S ? 0u : idx + 1;
+                                }
+                            }
                         }
+                        if (!__any_sync(0xffffffffu, state == 2)) break;
+                        // claim: every lane that stands at an empty slot tries once; a loser looks at the slot again (it may hold its key now)
+                        if (state == 2) {
+                            if (*(volatile u32*)t_count >= (u32)SkmWarpGeom<NW>::LIMIT) state = 3;
+                            else if (atomicCAS(&tkey[idx], EMPTY64, in.canon.w[0]) == EMPTY64) {
+#pragma unroll
+                                for (int w = 1; w < NW; w++) vkey[w * S + idx] = in.canon.w[w];
+                                vpay[idx] = payload_apply(PAYLOAD_FRESH, in.left, in.right);
+                                vrnk[idx] = rank;
+                                tlist[atomicAdd(t_count, 1u)] = (unsigned char)idx;
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(tab.slots + (table_hash(in.canon) & tab.mask)));
+                                state = 4;
+                            } else state = 0;
+                        }
+                        __syncwarp();   // claimed slots are complete before anybody probes them again
+                    }
+                    // update: a slot that only ONE lane of this step hits is a plain read-modify-write (nobody else touches this table)
+                    const unsigned hit = __ballot_sync(0xffffffffu, state == 1);
+                    if (state == 1) {
+                        const unsigned peers = __match_any_sync(hit, idx);
+                        if (peers == (1u << lane)) {
+                            const u64 p = vpay[idx];
+                            const u64 pn = payload_apply(p, in.left, in.right);
+                            if (pn != p) vpay[idx] = pn;
+                            if (rank < vrnk[idx]) vrnk[idx] = rank;
+                        } else st.apply(idx, in.left, in.right, rank);      // same k-mer several times in one step: atomics
+                    } else if (state == 3) {
+                        // the bucket holds more distinct k-mers than the table: this instance goes to HBM directly (same result)
+                        my_new += table_insert(tab, in.canon, in.left, in.right, rank);
+                        tot_spill++;
                     }
                     __syncwarp();
                 }
