@@ -123,8 +123,7 @@ public:
     void check_format_counter();
     // pass 1, aggregated (skm.cu): super-k-mer records scattered into the owners' arenas, one table update per DISTINCT k-mer
     int skm_mode_ = -1;          // -1 / 1: aggregated (default), 0: per-instance inserts (PGB200_SKM, world == 1 only)
-    int skm_warp_mode_ = 0;      // PGB200_SKM_WARP=1: one WARP per (8x smaller) bucket instead of one CTA per bucket (k_skm_apply_w)
-    int skm_flush_every_ = -1;   // single GPU: aggregate every n chunks (-1: host text 4, device text only when the arena is full)
+    int skm_flush_every_ = -1;   // single GPU: aggregate every n chunks (-1: host text whenever the insert stream is idle, device text only when the arena is full)
     SkmGeom skm_geom_;
     u32 skm_own_lo_ = 0, skm_own_hi_ = 0;
     int skm_own_shift_ = -1;

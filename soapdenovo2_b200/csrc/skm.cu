@@ -227,7 +227,9 @@ struct SmemTable {
                     vkey[idx] = k.w[0];
                     const u32 n = atomicAdd(count, 1u);
                     list[n] = (LT)idx;
+#ifndef SKM_NO_PREFETCH
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(tab.slots + (table_hash(k) & tab.mask)));
+#endif
                     return 2;
                 }
                 k0 = old;
@@ -336,7 +338,6 @@ struct SkmApplyArgs {
     u32* deferred;
 };
 constexpr u64 SKM_CREDIT = 1ull << 16;   // table room a CTA reserves at a time (keys)
-constexpr u64 SKM_CREDIT_W = 1ull << 12; // ... and a warp of the one-warp-per-bucket kernel (there are 10x more of them)
 
 __device__ __forceinline__ u64 shfl64(u64 v, int src) { return (u64)__shfl_sync(0xffffffffu, (unsigned long long)v, src); }
 
@@ -543,249 +544,6 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply(Table<NW> tab, 
     }
 }
 
-// ------------------------------------------------------------------------------------------------ aggregation, one WARP per bucket
-// Same work as k_skm_apply with the bucket sized for one warp (about 100 distinct k-mers: 8x more buckets) and a private
-// shared-memory table per warp.  Nothing in it is CTA-wide: no barrier, no waiting for the slowest warp of a bucket, and the fixed
-// cost of a bucket (segment ranges, table room, flush round trips) is paid by one warp while the other warps of the SM compute.
-template <int NW>
-struct SkmWarpGeom {
-    static constexpr int SLOTS = NW == 2 ? 200 : 110;
-    static constexpr int LIMIT = SLOTS - 40;              // 32 lanes claim concurrently
-    static constexpr int BYTES = ((NW + 2) * SLOTS * 8 + SLOTS + 32 * 12 + 16 + 15) & ~15;   // table, u8 claim list, 32 dense segment entries, count
-};
-template <int NW>
-__global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply_w(Table<NW> tab, KParams<NW> kp, SkmApplyArgs a) {
-    constexpr int RW = NW + 2, WARPS = SKM_APPLY_THREADS / 32, S = SkmWarpGeom<NW>::SLOTS;
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    unsigned char* mine = s_raw + (size_t)wid * SkmWarpGeom<NW>::BYTES;
-    u64* tkey = reinterpret_cast<u64*>(mine);
-    u64* tpay = tkey + NW * S;
-    u64* trnk = tpay + S;
-    const u64** d_ptr = reinterpret_cast<const u64**>(trnk + S);          // [32] dense segment entries: first record of the range
-    u32* d_pe = reinterpret_cast<u32*>(d_ptr + 32);                        // [32] its first record index inside the group
-    u32* t_count = d_pe + 32;
-    unsigned char* tlist = reinterpret_cast<unsigned char*>(t_count + 4);
-    SmemTable<NW, S, SkmWarpGeom<NW>::LIMIT, unsigned char> st{tkey, tpay, trnk, tlist, t_count};
-    volatile u64* vkey = tkey;
-    volatile u64* vpay = tpay;
-    volatile u64* vrnk = trnk;
-    const unsigned lane_le = 0xffffffffu >> (31 - lane);
-    for (int i = lane; i < S; i += 32) tkey[i] = EMPTY64;   // the flush re-empties what it merges
-    __syncwarp();
-    const int n_segs = (int)a.segs->n;
-    unsigned tot_new = 0, tot_spill = 0;
-    u64 credit = 0;                      // lane 0: table room this warp holds
-    const u32 n_warps = gridDim.x * WARPS;
-    for (u32 pos = blockIdx.x * WARPS + wid; pos < a.n_list; pos += n_warps) {
-        const u32 b = a.bucket_list ? a.bucket_list[pos] : pos;
-        // ---- records of the bucket (all segments) -> table room
-        u32 R = 0, c0 = 0;                 // c0 / ptr0: this lane's range in the first group of 32 segments (kept for the second pass)
-        const u64* ptr0 = nullptr;
-        for (int sg = 0; sg < n_segs; sg += 32) {
-            const int j = sg + lane;
-            u32 c = 0;
-            if (j < n_segs) {
-                const u32* so = a.segs->segoff[j];
-                const u32 lo = so[b];
-                c = so[b + 1] - lo;
-                if (sg == 0) { c0 = c; ptr0 = a.segs->recs[j] + (u64)lo * RW; }
-            }
-            R += __reduce_add_sync(0xffffffffu, c);
-        }
-        if (R == 0) continue;
-        int defer = 0;
-        if (lane == 0) {
-            const u64 bound = (u64)R * SKM_MAX_RUN;
-            if (credit < bound) {
-                unsigned long long* res = (unsigned long long*)&a.counters[C_RESERVED];
-                const u64 want = bound - credit, ask = want > SKM_CREDIT_W ? want : SKM_CREDIT_W;
-                u64 old = atomicAdd(res, (unsigned long long)ask);
-                if (old + ask <= a.limit) credit += ask;
-                else {
-                    atomicAdd(res, (unsigned long long)(0ull - ask));
-                    bool got = false;
-                    if (ask != want) {
-                        old = atomicAdd(res, (unsigned long long)want);
-                        if (old + want <= a.limit) { credit += want; got = true; }
-                        else atomicAdd(res, (unsigned long long)(0ull - want));
-                    }
-                    if (!got) {
-                        defer = 1;
-                        a.deferred[atomicAdd((unsigned long long*)&a.counters[C_DEFER], 1ull)] = b;
-                        atomicMax((unsigned long long*)&a.counters[C_MAXU], (unsigned long long)bound);
-                    }
-                }
-            }
-            if (!defer) credit -= bound;
-            *t_count = 0;
-        }
-        defer = __shfl_sync(0xffffffffu, defer, 0);
-        if (defer) continue;
-        unsigned my_new = 0;
-        for (int sg = 0; sg < n_segs; sg += 32) {
-            // the non-empty ranges of this group of segments, made dense: entry r = (first record pointer, first record index)
-            const int j = sg + lane;
-            u32 c = c0;
-            const u64* ptr = ptr0;
-            if (sg > 0) {
-                c = 0;
-                if (j < n_segs) {
-                    const u32* so = a.segs->segoff[j];
-                    const u32 lo = so[b];
-                    c = so[b + 1] - lo;
-                    ptr = a.segs->recs[j] + (u64)lo * RW;
-                }
-            }
-            u32 inc = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const u32 v = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += v;
-            }
-            const u32 T = __shfl_sync(0xffffffffu, inc, 31);      // records in this group
-            if (T == 0) continue;
-            const unsigned nz = __ballot_sync(0xffffffffu, c > 0);
-            const int nv = __popc(nz);
-            __syncwarp();
-            if (c > 0) {
-                const int r = __popc(nz & (lane_le >> 1));
-                d_ptr[r] = ptr;
-                d_pe[r] = inc - c;
-            }
-            __syncwarp();
-            const u32 my_pe = lane < nv ? d_pe[lane] : 0xFFFFFFFFu;
-            for (u32 rb = 0; rb < T; rb += 32) {
-                // ---- 32 consecutive records of the group, one per lane
-                const u32 q = rb + lane;
-                const bool valid = q < T;
-                u64 hdr = 0, x[NW + 1];
-#pragma unroll
-                for (int i = 0; i < NW + 1; i++) x[i] = 0;
-                {
-                    const unsigned starts = __reduce_or_sync(0xffffffffu, (lane < nv && my_pe > rb && my_pe - rb < 32u) ? 1u << (my_pe - rb) : 0u);
-                    const int first = __popc(__ballot_sync(0xffffffffu, lane < nv && my_pe <= rb)) - 1;
-                    if (valid) {
-                        const int src = first + __popc(starts & lane_le);
-                        const uint4* p = reinterpret_cast<const uint4*>(d_ptr[src] + (u64)(q - d_pe[src]) * RW);
-                        u64 w[RW];
-#pragma unroll
-                        for (int i = 0; i < RW / 2; i++) {
-                            const uint4 v = __ldg(p + i);
-                            w[2 * i] = (u64)v.x | ((u64)v.y << 32);
-                            w[2 * i + 1] = (u64)v.z | ((u64)v.w << 32);
-                        }
-                        hdr = w[0];
-#pragma unroll
-                        for (int i = 0; i < NW + 1; i++) x[i] = w[1 + i];
-                    }
-                }
-                const u32 n = valid ? (u32)skm_rec_n(hdr) : 0u;
-                u32 ic = n;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const u32 v = __shfl_up_sync(0xffffffffu, ic, d);
-                    if (lane >= d) ic += v;
-                }
-                const u32 I = __shfl_sync(0xffffffffu, ic, 31);
-                const u32 pe = ic - n;
-                for (u32 q0 = 0; q0 < I; q0 += 32) {
-                    const u32 qi = q0 + lane;
-                    const bool has = qi < I;
-                    const unsigned starts = __reduce_or_sync(0xffffffffu, (valid && pe > q0 && pe - q0 < 32u) ? 1u << (pe - q0) : 0u);
-                    const int first = __popc(__ballot_sync(0xffffffffu, valid && pe <= q0)) - 1;
-                    const int src = (first + __popc(starts & lane_le)) & 31;
-                    const int t = (int)(qi - __shfl_sync(0xffffffffu, pe, src));
-                    const u64 h = shfl64(hdr, src);
-                    u64 y[NW + 1];
-#pragma unroll
-                    for (int i = 0; i < NW + 1; i++) y[i] = shfl64(x[i], src);
-                    // ---- the warp owns this table: everything below is warp-synchronous (no BUSY protocol, no waiting on other warps)
-                    SkmInst<NW> in;
-                    u64 rank = 0;
-                    u32 idx = 0;
-                    int state = 5;                      // 0 searching | 1 key found at idx | 2 at an empty slot | 3 no room | 4 claimed | 5 no instance
-                    if (has) {
-                        in = skm_instance_rec<NW>(kp, h, y, t);
-                        rank = skm_rec_rank(h, t);
-                        idx = (u32)(((u64)skm_slot_hash(in.canon, 32) * (u64)S) >> 32);
-                        state = 0;
-                    }
-                    for (;;) {
-                        // search: one probe per trip for every lane still looking; the lanes stay together
-                        while (__any_sync(0xffffffffu, state == 0)) {
-                            if (state == 0) {
-                                const u64 k0 = vkey[idx];
-                                if (k0 == EMPTY64) state = 2;
-                                else {
-                                    bool same = k0 == in.canon.w[0];
-#pragma unroll
-                                    for (int w = 1; w < NW; w++) same = same && vkey[w * S + idx] == in.canon.w[w];
-                                    if (same) state = 1;
-                                    else idx = idx + 1 == (u32)S ? 0u : idx + 1;
-                                }
-                            }
-                        }
-                        if (!__any_sync(0xffffffffu, state == 2)) break;
-                        // claim: every lane that stands at an empty slot tries once; a loser looks at the slot again (it may hold its key now)
-                        if (state == 2) {
-                            if (*(volatile u32*)t_count >= (u32)SkmWarpGeom<NW>::LIMIT) state = 3;
-                            else if (atomicCAS(&tkey[idx], EMPTY64, in.canon.w[0]) == EMPTY64) {
-#pragma unroll
-                                for (int w = 1; w < NW; w++) vkey[w * S + idx] = in.canon.w[w];
-                                vpay[idx] = payload_apply(PAYLOAD_FRESH, in.left, in.right);
-                                vrnk[idx] = rank;
-                                tlist[atomicAdd(t_count, 1u)] = (unsigned char)idx;
-                                asm volatile("prefetch.global.L2 [%0];" ::"l"(tab.slots + (table_hash(in.canon) & tab.mask)));
-                                state = 4;
-                            } else state = 0;
-                        }
-                        __syncwarp();   // claimed slots are complete before anybody probes them again
-                    }
-                    // update: a slot that only ONE lane of this step hits is a plain read-modify-write (nobody else touches this table)
-                    const unsigned hit = __ballot_sync(0xffffffffu, state == 1);
-                    if (state == 1) {
-                        const unsigned peers = __match_any_sync(hit, idx);
-                        if (peers == (1u << lane)) {
-                            const u64 p = vpay[idx];
-                            const u64 pn = payload_apply(p, in.left, in.right);
-                            if (pn != p) vpay[idx] = pn;
-                            if (rank < vrnk[idx]) vrnk[idx] = rank;
-                        } else st.apply(idx, in.left, in.right, rank);      // same k-mer several times in one step: atomics
-                    } else if (state == 3) {
-                        // the bucket holds more distinct k-mers than the table: this instance goes to HBM directly (same result)
-                        my_new += table_insert(tab, in.canon, in.left, in.right, rank);
-                        tot_spill++;
-                    }
-                    __syncwarp();
-                }
-            }
-            __syncwarp();   // d_ptr / d_pe are rewritten by the next group
-        }
-        // ---- flush
-        const u32 n_claimed = *(volatile u32*)t_count;
-        for (u32 i = lane; i < n_claimed; i += 32) {
-            const u32 idx = tlist[i];
-            Kmer<NW> k;
-#pragma unroll
-            for (int w = 0; w < NW; w++) k.w[w] = tkey[w * S + idx];
-            my_new += table_merge(tab, k, tpay[idx], trnk[idx]);
-            tkey[idx] = EMPTY64;
-        }
-        const unsigned bucket_new = __reduce_add_sync(0xffffffffu, my_new);
-        tot_new += my_new;
-        if (lane == 0) credit += (u64)R * SKM_MAX_RUN - (u64)bucket_new;
-        __syncwarp();
-    }
-    if (lane == 0 && credit) atomicAdd((unsigned long long*)&a.counters[C_RESERVED], (unsigned long long)(0ull - credit));
-    tot_new = __reduce_add_sync(0xffffffffu, tot_new);
-    tot_spill = __reduce_add_sync(0xffffffffu, tot_spill);
-    if (lane == 0) {
-        if (tot_new) atomicAdd(&a.counters[C_DISTINCT], (u64)tot_new);
-        if (tot_spill) atomicAdd(&a.counters[C_MISC2], (u64)tot_spill);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------ host side
 template <int NW>
 static constexpr size_t skm_apply_smem() {
@@ -801,10 +559,7 @@ void EngineT<NW>::skm_init() {
     u64 est = 0;   // expected number of distinct k-mers on THIS GPU
     if (prm_.table_slots) est = prm_.table_slots / 2;
     else if (prm_.initG) est = (u64)((double)prm_.P * (double)ref_static_set_size(prm_.initG, prm_.P, prm_.flavour127 != 0) * 0.77) / world;
-    if (const char* e = getenv("PGB200_SKM_WARP")) skm_warp_mode_ = atoi(e);
-    // distinct k-mers a bucket should hold on average: half a CTA table, or 45 % of a warp table
-    const u64 per_bucket = skm_warp_mode_ ? (u64)(SkmWarpGeom<NW>::SLOTS * 45 / 100) : (u64)(SKM_SLOTS / 2);
-    u64 Bo = est ? next_pow2_u64((est + per_bucket - 1) / per_bucket) : (skm_warp_mode_ ? 1ull << 19 : 1ull << 16);
+    u64 Bo = est ? next_pow2_u64((est + SKM_SLOTS / 2 - 1) / (SKM_SLOTS / 2)) : (1ull << 16);   // half a shared-memory table per bucket on average
     if (Bo < 1024) Bo = 1024;
     u64 B = Bo * world;
     if (const char* e = getenv("PGB200_SKM_BUCKETS")) B = strtoull(e, nullptr, 0);
@@ -835,7 +590,6 @@ void EngineT<NW>::skm_init() {
         PG_CUDA(cudaFuncSetAttribute(k_skm_rescan<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
     }
     PG_CUDA(cudaFuncSetAttribute(k_skm_apply<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skm_apply_smem<NW>()));
-    PG_CUDA(cudaFuncSetAttribute(k_skm_apply_w<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((SKM_APPLY_THREADS / 32) * SkmWarpGeom<NW>::BYTES)));
     if (prm_.verbose) fprintf(stderr, "[pgb200] aggregated pass 1: %u buckets (%u owned by GPU %d of %d), minimizer length %d, window %d\n", skm_geom_.n_buckets,
                               skm_own_hi_ - skm_own_lo_, prm_.rank, world, skm_geom_.m, skm_geom_.w);
 }
@@ -972,9 +726,18 @@ void EngineT<NW>::skm_make_room(u64 n_rec, bool host_text) {
     skm_init();
     xchg_default_setup();
     if (xa_geom_.world == 1) {
-        const int every = skm_flush_every_ >= 0 ? skm_flush_every_ : (host_text ? 4 : 0);
+        // Host text arrives at PCIe speed and leaves the GPU idle most of the time: whenever the insert stream has drained and at least
+        // two chunks are waiting, they are aggregated right away, so that only the last couple of chunks remain for pgb200_finish_pass1.
+        // Device-resident text is fed faster than it is partitioned: the stream never drains and everything is aggregated once.
+        // PGB200_SKM_FLUSH_EVERY=n forces a fixed cadence (0: only when the arena is full).
+        bool early = false;
+        if (skm_flush_every_ > 0) early = xa_seg_idx_ >= (u32)skm_flush_every_;
+        else if (skm_flush_every_ < 0 && host_text && xa_seg_idx_ >= 2) {
+            early = cudaStreamQuery(st_) == cudaSuccess;
+            if (!early) cudaGetLastError();   // cudaErrorNotReady is not an error; do not leave it for the next launch check
+        }
         const bool full = xa_seg_idx_ >= xa_geom_.max_seg || skm_room_estimate(n_rec) > xa_geom_.cap_pair;
-        if ((full || (every > 0 && xa_seg_idx_ >= (u32)every)) && xa_seg_idx_ > 0) {
+        if ((full || early) && xa_seg_idx_ > 0) {
             skm_close_epoch(false);
             skm_flush();
         }
@@ -1072,15 +835,8 @@ void EngineT<NW>::skm_launch_apply(const u32* list, u32 n_list, u32* deferred_ou
     aa.segs = segs; aa.bucket_list = list; aa.n_list = n_list; aa.counters = d_cnt_;
     aa.limit = (u64)(0.85 * (double)cap_);
     aa.deferred = deferred_out;
-    if (skm_warp_mode_) {
-        const size_t smem = (size_t)(SKM_APPLY_THREADS / 32) * SkmWarpGeom<NW>::BYTES;
-        const unsigned per_sm = (unsigned)std::min<size_t>((227 * 1024) / (smem + 1024), 2048 / SKM_APPLY_THREADS);
-        const unsigned blocks = (unsigned)std::min<u64>(((u64)n_list + SKM_APPLY_THREADS / 32 - 1) / (SKM_APPLY_THREADS / 32), 148ull * per_sm);
-        if (blocks) k_skm_apply_w<NW><<<blocks, SKM_APPLY_THREADS, smem, st_>>>(tab_, kp_, aa);
-    } else {
-        const unsigned blocks = (unsigned)std::min<u64>((u64)n_list, 148ull * (NW == 2 ? 3 : 2));
-        if (blocks) k_skm_apply<NW><<<blocks, SKM_APPLY_THREADS, skm_apply_smem<NW>(), st_>>>(tab_, kp_, aa);
-    }
+    const unsigned blocks = (unsigned)std::min<u64>((u64)n_list, 148ull * (NW == 2 ? 3 : 2));
+    if (blocks) k_skm_apply<NW><<<blocks, SKM_APPLY_THREADS, skm_apply_smem<NW>(), st_>>>(tab_, kp_, aa);
     PG_CUDA(cudaGetLastError());
     PG_CUDA(cudaMemcpyAsync(h_flush_, d_cnt_ + C_XERR, 5 * sizeof(u64), cudaMemcpyDeviceToHost, st_));   // XERR, XUSED, RESERVED, DEFER, MAXU
     p1_.launches += 2;

@@ -50,18 +50,16 @@ PG_HD unsigned pl_twin(u64 p) { return (unsigned)((p >> PL_TWIN_SHIFT) & 3); }
 PG_HD unsigned pl_inedge(u64 p) { return (unsigned)((p >> PL_INEDGE_SHIFT) & 3); }
 
 // One instance applied to a payload word: set_new_kmer (newhash.c:123-140) when fresh, else update_kmer (:74-106)
-// + `single = 0` (newhash.c:509).  left/right are base codes 0..3 or 4 (= none).
+// + `single = 0` (newhash.c:509).  left/right are base codes 0..3 or 4 (= none).  Branch-free on the update path (the lanes of a
+// warp hold different neighbours and different counters): one increment word, with the increments of saturated fields removed.
 PG_HD u64 payload_apply(u64 p, unsigned left, unsigned right) {
-    if (p == PAYLOAD_FRESH) {
-        u64 n = (1ull << PL_COV_SHIFT) | PL_SINGLE;
-        if (left < 4) n |= 1ull << (6 * left);
-        if (right < 4) n |= 1ull << (PL_R_SHIFT + 6 * right);
-        return n;
-    }
-    if (left < 4 && pl_l(p, left) < 63) p += 1ull << (6 * left);
-    if (right < 4 && pl_r(p, right) < 63) p += 1ull << (PL_R_SHIFT + 6 * right);
-    if ((left < 4 || right < 4) && pl_cov(p) < 255) p += 1ull << PL_COV_SHIFT;
-    return p & ~PL_SINGLE;
+    const u64 il = left < 4 ? 1ull << (6 * left) : 0ull;
+    const u64 ir = right < 4 ? 1ull << (PL_R_SHIFT + 6 * right) : 0ull;
+    if (p == PAYLOAD_FRESH) return (1ull << PL_COV_SHIFT) | PL_SINGLE | il | ir;
+    const u64 ml = il * 63ull, mr = ir * 63ull, mc = 255ull << PL_COV_SHIFT;      // the fields the increments land in
+    u64 inc = ((p & ml) == ml ? 0ull : il) | ((p & mr) == mr ? 0ull : ir);
+    if ((il | ir) != 0ull && (p & mc) != mc) inc |= 1ull << PL_COV_SHIFT;
+    return (p + inc) & ~PL_SINGLE;
 }
 
 template <int NW>

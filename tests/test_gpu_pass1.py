@@ -15,16 +15,13 @@ def _build():
     util.build_oracle()
 
 
-@pytest.fixture(params=["direct", "aggregated", "aggregated_warp"], autouse=True)
+@pytest.fixture(params=["direct", "aggregated"], autouse=True)
 def _insert_mode(request, monkeypatch):
-    """Every case runs three times: per-instance inserts (k_chop_insert, PGB200_SKM=0), the default aggregated pass 1 (super-k-mer
-    records, one CTA per bucket, skm.cu) and its one-warp-per-bucket variant (PGB200_SKM_WARP=1)."""
+    """Every case runs twice: per-instance inserts (k_chop_insert, PGB200_SKM=0) and the default aggregated pass 1 (super-k-mer
+    records, skm.cu)."""
     monkeypatch.delenv("PGB200_SKM", raising=False)
-    monkeypatch.delenv("PGB200_SKM_WARP", raising=False)
     if request.param == "direct":
         monkeypatch.setenv("PGB200_SKM", "0")
-    elif request.param == "aggregated_warp":
-        monkeypatch.setenv("PGB200_SKM_WARP", "1")
 
 
 def _feed_cfg_files(eng, files, fastq, stride=1, base=0, **kw):
