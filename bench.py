@@ -7,7 +7,8 @@ table insert/count -> delow/mark-linear/kmerFreq sweeps) over the synthetic read
 
   value  : whole-job distinct k-mers / s with the FASTQ text already resident in HBM (device pointers through the C-ABI)
   e2e    : the same metric through the C-ABI with HOST (pinned) text buffers: H2D copies inside the timed region, plus a
-           D2H read of the coverage histogram / statistics every step.  Same kernels as `value` (aggregated pass 1).
+           D2H read of the coverage histogram / statistics every step.  N=1: the engine inserts host text per instance (that hides
+           under the copies; the aggregation cannot finish before the last chunk); N>1: the same aggregated kernels as `value`.
   roofline: the insert (k_skm_count/scatter + k_skm_apply, soapdenovo2_b200/csrc/skm.cu), HBM bound by SURVEY.md 8(d): algorithmic
            bytes = 64 B per k-mer instance (one 32 B slot sector read + written back); time = CUDA events recorded by the engine on
            its own stream around those launches.  The aggregated insert moves far fewer bytes than that (one table update per
@@ -479,7 +480,9 @@ def main():
                    "parallelism": (f"minimizer buckets owned in {world} contiguous ranges; chunk i decoded + partitioned by rank i % {world}; super-k-mer records stored straight into the "
                                    f"owner GPU's arena by the partition kernel (NVLink peer stores over CUDA IPC mappings, no library collective on the data path); one barrier per step"
                                    if world > 1 else "1 GPU"),
-                   "insert_mode": "aggregated pass 1 (super-k-mer records, one table update per distinct k-mer) for value AND e2e" if os.environ.get("PGB200_SKM", "1") != "0" else "PGB200_SKM=0: per-instance inserts",
+                   "insert_mode": ("aggregated pass 1 (super-k-mer records, one table update per distinct k-mer) for value AND e2e" if world > 1 or os.environ.get("PGB200_SKM") == "1"
+                                   else ("PGB200_SKM=0: per-instance inserts" if os.environ.get("PGB200_SKM") == "0"
+                                         else "value (text resident in HBM): aggregated pass 1, one table update per distinct k-mer; e2e (text over PCIe): per-instance inserts, hidden under the H2D copies -- see DESIGN.md section 5")),
                    "parity": parity, "digest": digest,
                    "l2_policy": f"inputs ({(t1.numel()+t2.numel())/1e9:.1f} GB text per rank, {st.table_slots*32*(2 if K>63 else 1)/1e9:.1f} GB table) are far larger than the 126 MB L2; the table is cleared every step"},
         "e2e": e2e, "gpu_launches": int(r["launches"]), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_b}))

@@ -298,7 +298,12 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     if (nbytes == 0) return;
     if (nbytes >= (1ull << 32)) throw std::runtime_error("pgb200: a text chunk must be smaller than 4 GiB (feed it in pieces)");
     PG_CUDA(cudaSetDevice(prm_.device));
-    const bool use_skm = prm_.world > 1 || skm_mode_ != 0;
+    // Which insert: several GPUs -> records (the only exchange format).  One GPU: text that is already in HBM -> aggregated (one HBM
+    // update per DISTINCT k-mer: 50 ms per 1.76e9 instances at configs[1]); text that arrives over PCIe -> per-instance inserts, which
+    // run at the DRAM update rate (100 ms for the same work) but hide completely under the 115 ms of H2D copies, whereas the aggregation
+    // can only finish after the last chunk (measured end to end: 134 ms vs 160-177 ms; aggregating mid-stream multiplies the HBM updates,
+    // profiles/r02_e2e_flush_cadence.md).  PGB200_SKM=0|1 forces one of them.
+    const bool use_skm = prm_.world > 1 || skm_mode_ > 0 || (skm_mode_ < 0 && on_device);
     cudaStream_t sd = use_skm ? st_dec_ : st_;   // the per-instance insert needs exact counters per chunk: one stream
     const unsigned char* d_text;
     const bool host_src = !on_device;

@@ -122,7 +122,7 @@ public:
     void chop_insert_chunk(const ReadChunk& ch);
     void check_format_counter();
     // pass 1, aggregated (skm.cu): super-k-mer records scattered into the owners' arenas, one table update per DISTINCT k-mer
-    int skm_mode_ = -1;          // -1 / 1: aggregated (default), 0: per-instance inserts (PGB200_SKM, world == 1 only)
+    int skm_mode_ = -1;          // -1: aggregated for device-resident text, per-instance inserts for host text; 0 / 1: forced (PGB200_SKM)
     int skm_flush_every_ = -1;   // single GPU: aggregate every n chunks (-1: host text whenever the insert stream is idle, device text only when the arena is full)
     SkmGeom skm_geom_;
     u32 skm_own_lo_ = 0, skm_own_hi_ = 0;

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(SKM_PART_THREADS) k_skm_rescan(SkmSendArgs a, 
 // Claim protocol: CAS(key0, EMPTY -> w0|BUSY), write the other key words + the first instance's payload and rank, fence, store w0.
 // A thread that meets a BUSY key0 whose other bits match waits for the publication (independent thread scheduling: the claimer makes
 // progress even inside the same warp).  The claimer also appends the slot to the claim list (the flush walks the list, not the
-// table) and prefetches the k-mer's home slot in the GLOBAL table into L2, so that the flush finds it there.
+// table).  (Prefetching the k-mer's home slot of the GLOBAL table into L2 at claim time measured no difference and was dropped.)
 // S slots (any size: the slot index is a multiply-shift range reduction of a 32-bit hash), claims stop at LIMIT so that the
 // table can never fill up completely whatever the number of concurrent claimers; LT = type of the claim-list entries.
 template <int NW, int S, int LIMIT, class LT>
@@ -227,9 +227,6 @@ struct SmemTable {
                     vkey[idx] = k.w[0];
                     const u32 n = atomicAdd(count, 1u);
                     list[n] = (LT)idx;
-#ifndef SKM_NO_PREFETCH
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(tab.slots + (table_hash(k) & tab.mask)));
-#endif
                     return 2;
                 }
                 k0 = old;

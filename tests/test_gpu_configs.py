@@ -43,7 +43,7 @@ def test_c2_shape_10mbp_pe_fastq_k63(tmp_path):
     cfg = synth.config_c2(str(tmp_path))
     ref, gpu = str(tmp_path / "ref"), str(tmp_path / "gpu")
     util.run([util.REF63, "pregraph", "-s", cfg, "-K", "63", "-p", "8", "-a", "2", "-R", "-o", ref], timeout=1500)
-    _engine(cfg, gpu, 63, 8, ("-a", "2", "-R"), env={"PGB200_CHUNK_MB": "64"})
+    _engine(cfg, gpu, 63, 8, ("-a", "2", "-R"), env={"PGB200_CHUNK_MB": "64", "PGB200_SKM": "1"})   # aggregated pass 1, several chunks
     util.compare(ref, gpu, util.SUFFIXES_R)
 
 

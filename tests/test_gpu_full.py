@@ -80,12 +80,12 @@ def test_multilib_k63_small_chunks(tmp_path):
     util.compare(ref, gpu, util.SUFFIXES_R)
 
 
-def test_multilib_k63_direct_pass1(tmp_path):
-    """The same multi-library case with pass 1 forced through the per-instance inserts (PGB200_SKM=0), several chunks."""
+def test_multilib_k63_aggregated_pass1(tmp_path):
+    """The same multi-library case with pass 1 forced through the aggregated path (super-k-mer records, skm.cu), several chunks."""
     cfg = synth.scenario_multilib(str(tmp_path))
     ref, gpu = str(tmp_path / "ref"), str(tmp_path / "gpu")
     _oracle(0, cfg, ref, 63, 8, ("-a", "1", "-R"))
-    _engine(0, cfg, gpu, 63, 8, ("-a", "1", "-R"), env={"PGB200_SKM": "0", "PGB200_CHUNK_MB": "1", "PGB200_TABLE_SLOTS": "4096"})
+    _engine(0, cfg, gpu, 63, 8, ("-a", "1", "-R"), env={"PGB200_SKM": "1", "PGB200_CHUNK_MB": "1", "PGB200_TABLE_SLOTS": "4096"})
     util.compare(ref, gpu, util.SUFFIXES_R)
 
 
@@ -118,9 +118,9 @@ def test_midsize_pe_k63_vs_reference(tmp_path):
     util.compare(ref, gpu, util.SUFFIXES_R)
     if util.have_ref():
         assert _counter_lines(lr) == _counter_lines(lg)
-    # and with the per-instance insert path (the default is the aggregated pass 1)
+    # and with the aggregated pass 1 (forced: the CLI feeds host text, which defaults to per-chunk inserts)
     gpu2 = str(tmp_path / "gpu2")
-    _engine(0, cfg, gpu2, 63, 8, ("-a", "2", "-R"), env={"PGB200_SKM": "0"})
+    _engine(0, cfg, gpu2, 63, 8, ("-a", "2", "-R"), env={"PGB200_SKM": "1"})
     util.compare(ref, gpu2, util.SUFFIXES_R)
 
 

@@ -17,11 +17,9 @@ def _build():
 
 @pytest.fixture(params=["direct", "aggregated"], autouse=True)
 def _insert_mode(request, monkeypatch):
-    """Every case runs twice: per-instance inserts (k_chop_insert, PGB200_SKM=0) and the default aggregated pass 1 (super-k-mer
-    records, skm.cu)."""
-    monkeypatch.delenv("PGB200_SKM", raising=False)
-    if request.param == "direct":
-        monkeypatch.setenv("PGB200_SKM", "0")
+    """Every case runs twice: per-instance inserts (k_chop_insert, the default for host text) and the aggregated pass 1 (super-k-mer
+    records, skm.cu: the default for device-resident text and the only path across GPUs), both forced through PGB200_SKM."""
+    monkeypatch.setenv("PGB200_SKM", "0" if request.param == "direct" else "1")
 
 
 def _feed_cfg_files(eng, files, fastq, stride=1, base=0, **kw):
@@ -125,7 +123,7 @@ def test_aggregated_stress_paths(tmp_path, monkeypatch, K, flav, buckets, arena_
     until the tiny global table has grown), a 1 MB arena (mid-stream flushes because the arena is full), periodic flushes, many
     small chunks.  Same table dump as the oracle."""
     if os.environ.get("PGB200_SKM") == "0":
-        pytest.skip("aggregated paths only")
+        pytest.skip("aggregated path only")
     if buckets != "0":
         monkeypatch.setenv("PGB200_SKM_BUCKETS", buckets)
     if arena_mb != "0":
