@@ -24,6 +24,9 @@ constexpr int SKM_APPLY_THREADS = 256;
 #ifndef SKM_LOG2_SLOTS
 #define SKM_LOG2_SLOTS 11
 #endif
+#ifndef SKM_APPLY_MIN_BLOCKS
+#define SKM_APPLY_MIN_BLOCKS 1
+#endif
 constexpr int SKM_SLOTS = 1 << SKM_LOG2_SLOTS;                       // shared-memory table slots per CTA (32 B/slot at K<=63: 64 KB, 3 CTAs per SM)
 constexpr int SKM_SOFT_LIMIT = SKM_SLOTS - SKM_APPLY_THREADS - 64;   // claims stop here: the table can never fill up completely
 constexpr int SKM_SIDE_RUNS = 16;
@@ -345,7 +348,7 @@ __device__ __forceinline__ u64 shfl64(u64 v, int src) { return (u64)__shfl_sync(
 // barrier and no staging buffer inside a bucket; the next batch's records and the next bucket's segment ranges are loaded while the
 // current ones are processed.
 template <int NW>
-__global__ void __launch_bounds__(SKM_APPLY_THREADS) k_skm_apply(Table<NW> tab, KParams<NW> kp, SkmApplyArgs a) {
+__global__ void __launch_bounds__(SKM_APPLY_THREADS, SKM_APPLY_MIN_BLOCKS) k_skm_apply(Table<NW> tab, KParams<NW> kp, SkmApplyArgs a) {
     constexpr int RW = NW + 2, WARPS = SKM_APPLY_THREADS / 32;
     extern __shared__ __align__(16) u64 s_dyn[];   // key[NW][S], pay[S], rnk[S], list[S] (u16)
     __shared__ const u64* s_ptr[SKM_MAX_SEGS];
@@ -832,7 +835,11 @@ void EngineT<NW>::skm_launch_apply(const u32* list, u32 n_list, u32* deferred_ou
     aa.segs = segs; aa.bucket_list = list; aa.n_list = n_list; aa.counters = d_cnt_;
     aa.limit = (u64)(0.85 * (double)cap_);
     aa.deferred = deferred_out;
-    const unsigned blocks = (unsigned)std::min<u64>((u64)n_list, 148ull * (NW == 2 ? 3 : 2));
+    int per_sm = 0, n_sm = 148;
+    PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_skm_apply<NW>, SKM_APPLY_THREADS, skm_apply_smem<NW>()));
+    PG_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, prm_.device));
+    if (per_sm < 1) per_sm = 1;
+    const unsigned blocks = (unsigned)std::min<u64>((u64)n_list, (u64)n_sm * per_sm);   // persistent CTAs: as many as are resident
     if (blocks) k_skm_apply<NW><<<blocks, SKM_APPLY_THREADS, skm_apply_smem<NW>(), st_>>>(tab_, kp_, aa);
     PG_CUDA(cudaGetLastError());
     PG_CUDA(cudaMemcpyAsync(h_flush_, d_cnt_ + C_XERR, 5 * sizeof(u64), cudaMemcpyDeviceToHost, st_));   // XERR, XUSED, RESERVED, DEFER, MAXU
