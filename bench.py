@@ -303,6 +303,7 @@ def main():
         t1, t2 = gen_pe_fastq_gpu(torch, dev, total_genome, n_pairs, seed=42)
         pair_base = 0
     torch.cuda.synchronize()
+    torch.cuda.empty_cache()   # hand the generator's temporaries back: the engine allocates with cudaMalloc
     chunk_reads = args.chunk_reads
     if not chunk_reads:
         if weak:

@@ -1,0 +1,85 @@
+/* contig_sidecar.c -- f2: the `contig` side of the pregraph -> contig hand-over, without the gzip'ed text.
+ *
+ * The engine can write the edges it builds as a binary sidecar `<prefix>.edge.b200` next to the byte-identical `.edge.gz`
+ * (PGB200_EDGE_SIDECAR=1; format below and in include/pregraph_b200.h).  This file is the reader a maintainer adds to SOAPdenovo2:
+ * a `loadEdge()` that fills `edge_array` from the sidecar exactly as the reference's text loader does (loadPreGraph.c:448-544:
+ * same allocation, same fields, same buildReverseComplementEdge / createArcMemo / loadPreArcs calls) and falls back to that loader
+ * when there is no sidecar.  Nothing of the reference is modified in source: scripts/link_dropin.sh renames the original symbol in
+ * the reference's OWN object (`objcopy --redefine-sym loadEdge=loadEdge_text loadPreGraph.o`) and links this file beside it.
+ * It is compiled against the reference's headers where they lie (-I$REF/standardPregraph/inc, -DMER63 | -DMER127), like oracle/_ref.
+ *
+ * Sidecar: 48-byte header { char magic[8] = "PGB2EDGE"; u32 version = 1; u32 K; u32 kmer_words (2 | 4); u32 reserved; u64 n_records;
+ * u64 num_ed; u64 reserved }, then per record { i32 length; i32 cvg; i32 bal_ed; u32 seq_bytes = length / 4 + 1;
+ * u64 from[kmer_words]; u64 to[kmer_words]; u8 seq[seq_bytes] (4 bases per byte, first base in bits 7:6: writeChar2tightString) }.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "stdinc.h"
+#include "newhash.h"
+#include "kmerhash.h"
+#include "extfunc.h"
+#include "extvab.h"
+
+extern void loadEdge_text(char *graphfile);   /* the reference's loadEdge, renamed at link time */
+extern void loadPreArcs(char *graphfile);
+
+typedef struct {
+    char magic[8];
+    unsigned int version, K, kmer_words, reserved0;
+    unsigned long long n_records, num_ed, reserved1;
+} SidecarHeader;
+
+void loadEdge(char *graphfile)
+{
+    char name[512];
+    FILE *fp;
+    SidecarHeader h;
+    unsigned long long r;
+    int index = -1;
+    unsigned int j;
+    snprintf(name, sizeof name, "%s.edge.b200", graphfile);
+    fp = fopen(name, "rb");
+    if (!fp) { loadEdge_text(graphfile); return; }
+    if (fread(&h, sizeof h, 1, fp) != 1 || memcmp(h.magic, "PGB2EDGE", 8) != 0 || h.version != 1 || h.kmer_words != sizeof(Kmer) / 8) {
+        fprintf(stderr, "%s is not an edge sidecar of this build; reading %s.edge.gz instead.\n", name, graphfile);
+        fclose(fp);
+        loadEdge_text(graphfile);
+        return;
+    }
+    num_ed_limit = 1.2 * num_ed;
+    edge_array = (EDGE *)ckalloc((num_ed_limit + 3) * sizeof(EDGE));
+    for (j = num_ed + 1; j <= num_ed_limit; j++) edge_array[j].seq = NULL;
+    for (r = 0; r < h.n_records; r++) {
+        int rec[4];
+        Kmer from_kmer, to_kmer;
+        char *tightSeq;
+        unsigned int edgeno;
+        if (fread(rec, sizeof rec, 1, fp) != 1 || fread(&from_kmer, sizeof(Kmer), 1, fp) != 1 || fread(&to_kmer, sizeof(Kmer), 1, fp) != 1) {
+            fprintf(stderr, "%s is truncated.\n", name);
+            exit(-1);
+        }
+        tightSeq = (char *)ckalloc((rec[0] / 4 + 1) * sizeof(char));
+        if (fread(tightSeq, 1, (size_t)rec[3], fp) != (size_t)rec[3]) { fprintf(stderr, "%s is truncated.\n", name); exit(-1); }
+        index++;
+        edgeno = index + 1;
+        edge_array[edgeno].length = rec[0];
+        edge_array[edgeno].cvg = rec[1];
+        edge_array[edgeno].from_vt = kmer2vt(from_kmer);
+        edge_array[edgeno].to_vt = kmer2vt(to_kmer);
+        edge_array[edgeno].seq = tightSeq;
+        edge_array[edgeno].bal_edge = rec[2] + 1;
+        edge_array[edgeno].rv = NULL;
+        edge_array[edgeno].arcs = NULL;
+        edge_array[edgeno].flag = 0;
+        edge_array[edgeno].deleted = 0;
+        if (rec[2]) {
+            buildReverseComplementEdge(edgeno);
+            index++;
+        }
+    }
+    fclose(fp);
+    fprintf(stderr, "%d edge(s) input.\n", index + 1);
+    createArcMemo();
+    loadPreArcs(graphfile);
+}

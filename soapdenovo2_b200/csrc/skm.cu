@@ -21,13 +21,16 @@ namespace pgb {
 
 constexpr int SKM_PART_THREADS = 128;
 constexpr int SKM_APPLY_THREADS = 256;
+// Shared-memory table of a bucket: 1024 slots (32 KB at K <= 63) and at most 42 registers per thread put 6 CTAs = 48 warps on an SM;
+// measured at configs[1] (gpurun_out/i_bench_*.json): 2048 slots / 3 CTAs 50.4 ms, 1024 / 6 CTAs 47.8 ms, 512 / 8 CTAs (32 registers,
+// spills) 51.7 ms per 1.76e9 instances.  256-bit keys (48 B slots, 78 live registers) stay at 3 CTAs.
 #ifndef SKM_LOG2_SLOTS
-#define SKM_LOG2_SLOTS 11
+#define SKM_LOG2_SLOTS 10
 #endif
 #ifndef SKM_APPLY_MIN_BLOCKS
-#define SKM_APPLY_MIN_BLOCKS 1
+#define SKM_APPLY_MIN_BLOCKS(NW) ((NW) == 2 ? 6 : 3)
 #endif
-constexpr int SKM_SLOTS = 1 << SKM_LOG2_SLOTS;                       // shared-memory table slots per CTA (32 B/slot at K<=63: 64 KB, 3 CTAs per SM)
+constexpr int SKM_SLOTS = 1 << SKM_LOG2_SLOTS;                       // shared-memory table slots per CTA
 constexpr int SKM_SOFT_LIMIT = SKM_SLOTS - SKM_APPLY_THREADS - 64;   // claims stop here: the table can never fill up completely
 constexpr int SKM_SIDE_RUNS = 16;
 constexpr int SKM_MAXW = 16;                                         // GPUs of one box
@@ -348,7 +351,7 @@ __device__ __forceinline__ u64 shfl64(u64 v, int src) { return (u64)__shfl_sync(
 // barrier and no staging buffer inside a bucket; the next batch's records and the next bucket's segment ranges are loaded while the
 // current ones are processed.
 template <int NW>
-__global__ void __launch_bounds__(SKM_APPLY_THREADS, SKM_APPLY_MIN_BLOCKS) k_skm_apply(Table<NW> tab, KParams<NW> kp, SkmApplyArgs a) {
+__global__ void __launch_bounds__(SKM_APPLY_THREADS, SKM_APPLY_MIN_BLOCKS(NW)) k_skm_apply(Table<NW> tab, KParams<NW> kp, SkmApplyArgs a) {
     constexpr int RW = NW + 2, WARPS = SKM_APPLY_THREADS / 32;
     extern __shared__ __align__(16) u64 s_dyn[];   // key[NW][S], pay[S], rnk[S], list[S] (u16)
     __shared__ const u64* s_ptr[SKM_MAX_SEGS];
@@ -610,7 +613,7 @@ void EngineT<NW>::xchg_setup(uint64_t cap_records) {
     }
     u64 cap_pair = cap_records / world;
     if (cap_pair < 4096) cap_pair = 4096;
-    u32 max_seg = SKM_MAX_SEGS / (world > 1 ? 1 : 1);
+    u32 max_seg = (u32)(SKM_MAX_SEGS / world);   // an aggregation launch reads at most SKM_MAX_SEGS segments over all senders
     if (const char* e = getenv("PGB200_SKM_MAX_SEG")) max_seg = (u32)atoi(e);
     if (max_seg < 1) max_seg = 1;
     if (max_seg > (u32)SKM_MAX_SEGS) max_seg = SKM_MAX_SEGS;
