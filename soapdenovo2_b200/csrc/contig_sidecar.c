@@ -21,8 +21,67 @@
 #include "extfunc.h"
 #include "extvab.h"
 
-extern void loadEdge_text(char *graphfile);   /* the reference's loadEdge, renamed at link time */
-extern void loadPreArcs(char *graphfile);
+extern void loadEdge_text(char *graphfile);                 /* the reference's loadEdge, renamed at link time */
+extern void buildReverseComplementEdge(unsigned int edgeno);  /* static in loadPreGraph.c; made global in the object at link time */
+
+/* The reference keeps loadPreArcs / add1Arc static (loadPreGraph.c:30, 580-641, 658-685) and inlines them into its loadEdge, so
+ * their logic is restated here: one line of <prefix>.preArc = "from to weight to weight ..."; an arc from->to implies the arc
+ * twin(to)->twin(from); existing arcs only gain multiplicity; new arcs are pushed at the head of the edge's list. */
+static void sidecar_add_arc(unsigned int from_ed, unsigned int to_ed, unsigned int weight)
+{
+    unsigned int bal_fe, bal_te;
+    ARC *parc, *bal_parc;
+    if (edge_array[from_ed].to_vt != edge_array[to_ed].from_vt) return;
+    bal_fe = getTwinEdge(from_ed);
+    bal_te = getTwinEdge(to_ed);
+    if (from_ed > num_ed || to_ed > num_ed || bal_fe > num_ed || bal_te > num_ed) return;
+    parc = getArcBetween(from_ed, to_ed);
+    if (parc) {
+        parc->multiplicity += weight;
+        parc->bal_arc->multiplicity += weight;
+        return;
+    }
+    parc = allocateArc(to_ed);
+    parc->multiplicity = weight;
+    parc->prev = NULL;
+    if (edge_array[from_ed].arcs) edge_array[from_ed].arcs->prev = parc;
+    parc->next = edge_array[from_ed].arcs;
+    edge_array[from_ed].arcs = parc;
+    if (bal_te == from_ed) {            /* A -> A': the arc is its own twin */
+        parc->bal_arc = parc;
+        parc->multiplicity += weight;
+        return;
+    }
+    bal_parc = allocateArc(bal_fe);
+    bal_parc->multiplicity = weight;
+    bal_parc->prev = NULL;
+    if (edge_array[bal_te].arcs) edge_array[bal_te].arcs->prev = bal_parc;
+    bal_parc->next = edge_array[bal_te].arcs;
+    edge_array[bal_te].arcs = bal_parc;
+    parc->bal_arc = bal_parc;
+    bal_parc->bal_arc = parc;
+}
+static void sidecar_load_prearcs(char *graphfile)
+{
+    char name[512], line[1024], *seg;
+    FILE *fp;
+    snprintf(name, sizeof name, "%s.preArc", graphfile);
+    fp = ckopen(name, "r");
+    arcCounter = 0;
+    while (fgets(line, sizeof line, fp) != NULL) {
+        unsigned int from_ed, target, weight;
+        seg = strtok(line, " ");
+        from_ed = atoi(seg);
+        while ((seg = strtok(NULL, " ")) != NULL) {
+            target = atoi(seg);
+            seg = strtok(NULL, " ");
+            weight = atoi(seg);
+            sidecar_add_arc(from_ed, target, weight);
+        }
+    }
+    fprintf(stderr, "%lli pre-arcs loaded.\n", arcCounter);
+    fclose(fp);
+}
 
 typedef struct {
     char magic[8];
@@ -81,5 +140,5 @@ void loadEdge(char *graphfile)
     fclose(fp);
     fprintf(stderr, "%d edge(s) input.\n", index + 1);
     createArcMemo();
-    loadPreArcs(graphfile);
+    sidecar_load_prearcs(graphfile);
 }

@@ -164,12 +164,93 @@ static void write_edge_gz(const std::string& name, const std::string& text) {
     gzclose(gz);
 }
 
+// f2: the edges as a binary sidecar for a `contig` that links csrc/contig_sidecar.c (format: include/pregraph_b200.h).  Converts the
+// edge TEXT the GPU emitted (">length L,<from>,<to>,cvg C, B" + bases, output_pregraph.c:88-110) -- host only, no GPU involved.
+static bool parse_hex_words(const char*& p, const char* end, uint64_t* w, int n) {
+    for (int i = 0; i < n; i++) {
+        uint64_t v = 0;
+        int digits = 0;
+        while (p < end) {
+            char c = *p;
+            int d = c >= '0' && c <= '9' ? c - '0' : (c >= 'a' && c <= 'f' ? c - 'a' + 10 : -1);
+            if (d < 0) break;
+            v = (v << 4) | (uint64_t)d;
+            p++; digits++;
+        }
+        if (!digits) return false;
+        w[i] = v;
+        if (i + 1 < n) { if (p >= end || *p != ' ') return false; p++; }
+    }
+    return true;
+}
+static bool parse_int(const char*& p, const char* end, long long* out) {
+    long long v = 0;
+    int digits = 0;
+    while (p < end && *p >= '0' && *p <= '9') { v = v * 10 + (*p - '0'); p++; digits++; }
+    *out = v;
+    return digits > 0;
+}
+static bool expect(const char*& p, const char* end, const char* lit) {
+    size_t n = strlen(lit);
+    if ((size_t)(end - p) < n || memcmp(p, lit, n) != 0) return false;
+    p += n;
+    return true;
+}
+extern "C" int pgb200_edge_text_to_sidecar(const char* text, size_t nbytes, int K, int flavour127, uint64_t num_ed, const char* path) {
+    try {
+        const int kw = flavour127 ? 4 : 2;
+        std::string out;
+        out.reserve(nbytes / 3 + 4096);
+        struct { char magic[8]; uint32_t version, K, kmer_words, r0; uint64_t n_records, num_ed, r1; } h;
+        memset(&h, 0, sizeof h);
+        memcpy(h.magic, "PGB2EDGE", 8);
+        h.version = 1; h.K = (uint32_t)K; h.kmer_words = (uint32_t)kw; h.num_ed = num_ed;
+        out.append(reinterpret_cast<const char*>(&h), sizeof h);
+        const char* p = text;
+        const char* end = text + nbytes;
+        uint64_t n_rec = 0;
+        while (p < end) {
+            long long length, cvg, bal;
+            uint64_t from[4], to[4];
+            if (!expect(p, end, ">length ") || !parse_int(p, end, &length) || !expect(p, end, ",") || !parse_hex_words(p, end, from, kw) || !expect(p, end, ",") ||
+                !parse_hex_words(p, end, to, kw) || !expect(p, end, ",cvg ") || !parse_int(p, end, &cvg) || !expect(p, end, ", ") || !parse_int(p, end, &bal) ||
+                !expect(p, end, "\n"))
+                throw std::runtime_error("pgb200: edge text does not parse (record " + std::to_string(n_rec) + ")");
+            int32_t rec[4] = {(int32_t)length, (int32_t)cvg, (int32_t)bal, (int32_t)(length / 4 + 1)};
+            out.append(reinterpret_cast<const char*>(rec), sizeof rec);
+            out.append(reinterpret_cast<const char*>(from), kw * 8);
+            out.append(reinterpret_cast<const char*>(to), kw * 8);
+            const size_t seq0 = out.size();
+            out.append((size_t)rec[3], '\0');
+            long long pos = 0;
+            while (pos < length) {
+                if (p >= end) throw std::runtime_error("pgb200: edge text ends inside a sequence");
+                const char c = *p++;
+                if (c == '\n') continue;
+                const unsigned code = ((unsigned)c & 6u) >> 1;                       // base2int, inc/def.h:39
+                out[seq0 + (size_t)(pos >> 2)] |= (char)(code << (6 - 2 * (pos & 3)));   // writeChar2tightString, seq.c:81-107
+                pos++;
+            }
+            if (p < end && *p == '\n') p++;
+            n_rec++;
+        }
+        reinterpret_cast<decltype(h)*>(&out[0])->n_records = n_rec;
+        write_file(path, out.data(), out.size());
+    } catch (const std::exception& ex) {
+        g_err = ex.what();
+        return -1;
+    }
+    return 0;
+}
+
 extern "C" int pgb200_kmer2edges(pgb200_engine* e, const char* prefix, pgb200_graph_stats* st) {
     PG_TRY
     EdgeStats es;
     std::string text;
     e->e->build_edges(&es, &text);
     write_edge_gz(std::string(prefix) + ".edge.gz", text);
+    if (getenv("PGB200_EDGE_SIDECAR") && pgb200_edge_text_to_sidecar(text.data(), text.size(), e->prm.K, e->prm.flavour127, es.num_ed, (std::string(prefix) + ".edge.b200").c_str()))
+        throw std::runtime_error(g_err);
     fprintf(stderr, "%llu (%llu) edge(s) and %llu extra node(s) constructed.\n", (unsigned long long)es.num_ed, (unsigned long long)es.edges,
             (unsigned long long)es.extra_nodes);
     if (st) { st->num_ed = es.num_ed; st->edges = es.edges; st->extra_nodes = es.extra_nodes; }
@@ -558,7 +639,15 @@ extern "C" int pgb200_pregraph_main(int argc, char** argv, int flavour127) {
         fprintf(stderr, "%llu (%llu) edge(s) and %llu extra node(s) constructed.\n", (unsigned long long)es.num_ed, (unsigned long long)es.edges,
                 (unsigned long long)es.extra_nodes);
         gs.num_ed = es.num_ed; gs.edges = es.edges; gs.extra_nodes = es.extra_nodes;
-        gz_thread = std::thread([&]() { try { write_edge_gz(prefix + ".edge.gz", edge_text); } catch (const std::exception& ex) { gz_error = ex.what(); } });
+        const uint64_t ne = es.num_ed;
+        gz_thread = std::thread([&, ne]() {
+            try {
+                // the binary sidecar first (a fraction of a second): a contig that links contig_sidecar.c never waits for the gzip
+                if (getenv("PGB200_EDGE_SIDECAR") && pgb200_edge_text_to_sidecar(edge_text.data(), edge_text.size(), prm.K, flavour127, ne, (prefix + ".edge.b200").c_str()))
+                    throw std::runtime_error(pgb200_last_error());
+                write_edge_gz(prefix + ".edge.gz", edge_text);
+            } catch (const std::exception& ex) { gz_error = ex.what(); }
+        });
     } catch (const std::exception& ex) { fprintf(stderr, "pgb200: edges failed: %s\n", ex.what()); exit(-1); }
     fprintf(stderr, "Time spent on constructing edges: %ds.\n\n", (int)(now_s() - t0));
     // ---- pass 2 (prlRead2edge)

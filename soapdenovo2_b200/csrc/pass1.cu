@@ -271,10 +271,12 @@ void EngineT<NW>::reset_pass1() {
     total_records_ = 0;
     p1_ = Pass1Stats();
     PG_CUDA(cudaMemsetAsync(d_cnt_, 0, C_COUNT * sizeof(u64), st_));
-    if (tab_.slots) PG_CUDA(cudaMemsetAsync(tab_buf_.p, 0xFF, cap_ * sizeof(Slot<NW>), st_));
     order_buf_.release();
     n_nodes_ = 0;
     sync();
+    // the table is cleared on the insert stream WITHOUT waiting: the next pass starts with decoding (another stream), and whatever
+    // touches the table next is ordered behind this memset by the stream
+    if (tab_.slots) PG_CUDA(cudaMemsetAsync(tab_buf_.p, 0xFF, cap_ * sizeof(Slot<NW>), st_));
     for (int i = 0; i < C_COUNT; i++) h_cnt_[i] = 0;
     if (prm_.verbose >= 2) fprintf(stderr, "[pgb200] reset_pass1: %.2f ms host\n", host_now() - t0);
 }

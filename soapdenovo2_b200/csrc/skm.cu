@@ -126,14 +126,24 @@ __global__ void __launch_bounds__(256) k_skm_publish(SkmSendArgs a) {
     }
 }
 
+// A record goes out with as few stores as possible: ONE 256-bit store per 32 bytes (STG.E.256 on sm_100a) -- over NVLink every store
+// is a packet, and 32-byte packets measured at only ~200 GB/s when a record was two 16-byte stores.
+__device__ __forceinline__ void st256(u64* dst, u64 a, u64 b, u64 c, u64 d) {
+    asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
 template <int NW>
 __device__ __forceinline__ void skm_store_rec(u64* dst, const SkmRec<NW>& r) {
+    if (NW == 2) {
+        st256(dst, r.w[0], r.w[1], r.w[2], r.w[3]);                       // 32-byte records are 32-byte aligned
+    } else {
+        // 48-byte records: 16-byte aligned only
 #pragma unroll
-    for (int p = 0; p < (NW + 2) / 2; p++) {
-        uint4 v;
-        v.x = (unsigned)r.w[2 * p]; v.y = (unsigned)(r.w[2 * p] >> 32);
-        v.z = (unsigned)r.w[2 * p + 1]; v.w = (unsigned)(r.w[2 * p + 1] >> 32);
-        reinterpret_cast<uint4*>(dst)[p] = v;
+        for (int p = 0; p < (NW + 2) / 2; p++) {
+            uint4 v;
+            v.x = (unsigned)r.w[2 * p]; v.y = (unsigned)(r.w[2 * p] >> 32);
+            v.z = (unsigned)r.w[2 * p + 1]; v.w = (unsigned)(r.w[2 * p + 1] >> 32);
+            reinterpret_cast<uint4*>(dst)[p] = v;
+        }
     }
 }
 template <int NW>

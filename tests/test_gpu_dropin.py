@@ -51,3 +51,26 @@ def test_all_pipeline_in_one_process(tmp_path):
         util.run([exe, "all", "-s", cfg, "-K", "31", "-p", "1", "-a", "1", "-R", "-o", out], timeout=240)
         outs[tag] = out
     util.compare(outs["ref"], outs["gpu"], util.SUFFIXES_R + ["contig", "Arc", "updated.edge", "ContigIndex", "scafSeq", "scaf", "links", "newContigIndex"])
+
+
+def test_stage_writes_the_edge_sidecar_and_contig_reads_it(tmp_path):
+    """f2: with PGB200_EDGE_SIDECAR=1 the GPU stage also writes <prefix>.edge.b200; it must equal what the host converter makes from
+    the stage's own (byte-identical) .edge.gz, and the reference's `contig`, linked with csrc/contig_sidecar.c, must build the same
+    contigs from it WITHOUT the .edge.gz."""
+    import shutil
+    from soapdenovo2_b200 import api
+    cfg = synth.scenario_multilib(str(tmp_path))
+    ref, gpu = str(tmp_path / "ref"), str(tmp_path / "gpu")
+    util.run([util.REF63, "pregraph", "-s", cfg, "-K", "63", "-p", "8", "-a", "1", "-R", "-o", ref])
+    r = subprocess.run([B63, "pregraph", "-s", cfg, "-K", "63", "-p", "8", "-a", "1", "-R", "-o", gpu], capture_output=True, text=True,
+                       env=dict(os.environ, PGB200_EDGE_SIDECAR="1"), timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    util.compare(ref, gpu, util.SUFFIXES_R)
+    side = open(gpu + ".edge.b200", "rb").read()
+    shutil.copy(gpu + ".edge.b200", gpu + ".edge.b200.stage")
+    api.edge_gz_to_sidecar(gpu, 63, 0)
+    assert open(gpu + ".edge.b200", "rb").read() == side
+    os.remove(gpu + ".edge.gz")
+    util.run([util.REF63, "contig", "-g", ref, "-R"])
+    util.run([B63, "contig", "-g", gpu, "-R"])
+    util.compare(ref, gpu, ["contig", "Arc", "updated.edge", "ContigIndex"])
