@@ -6,7 +6,7 @@
  * same allocation, same fields, same buildReverseComplementEdge / createArcMemo / loadPreArcs calls) and falls back to that loader
  * when there is no sidecar.  Nothing of the reference is modified in source: scripts/link_dropin.sh renames the original symbol in
  * the reference's OWN object (`objcopy --redefine-sym loadEdge=loadEdge_text loadPreGraph.o`) and links this file beside it.
- * It is compiled against the reference's headers where they lie (-I$REF/standardPregraph/inc, -DMER63 | -DMER127), like oracle/_ref.
+ * It is compiled against the reference's headers where they lie (-I$REF/standardPregraph/inc, -DMER63 | -DMER127).
  *
  * Sidecar: 48-byte header { char magic[8] = "PGB2EDGE"; u32 version = 1; u32 K; u32 kmer_words (2 | 4); u32 reserved; u64 n_records;
  * u64 num_ed; u64 reserved }, then per record { i32 length; i32 cvg; i32 bal_ed; u32 seq_bytes = length / 4 + 1;
