@@ -100,7 +100,7 @@ public:
     u64* h_cnt_ = nullptr;      // pinned mirror
 
     // decode scratch
-    DevBuf text_bufs_[2], line_buf_, scan_buf_;
+    DevBuf text_bufs_[2], line_buf_, scan_buf_, hist_buf_;
     int text_flip_ = 0;
     cudaStream_t st_copy_ = nullptr;   // H2D of chunk i+1 overlaps the insert of chunk i
     cudaEvent_t ev_copy_ = nullptr;

@@ -321,8 +321,8 @@ template <int NW>
 void EngineT<NW>::sweeps(SweepStats* st) {
     double t0 = host_now();
     create_table_if_needed();
-    DevBuf hist;
-    hist.alloc(256 * sizeof(u64));
+    DevBuf& hist = hist_buf_;   // persistent: a cudaMalloc / cudaFree pair per call costs more than the sweep of a small table
+    hist.ensure(256 * sizeof(u64));
     PG_CUDA(cudaMemsetAsync(hist.p, 0, 256 * sizeof(u64), st_));
     PG_CUDA(cudaMemsetAsync(d_cnt_ + C_LINEAR, 0, 2 * sizeof(u64), st_));
     int D = (int)(signed char)prm_.D;   // deLowKmer is a `char` (inc/global.h:67)
