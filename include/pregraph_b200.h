@@ -9,8 +9,11 @@
  *   call_pregraph                 int call_pregraph(int argc, char **argv)            pregraph.c:62  (declared main.c:29,
  *                                 called main.c:74 and main.c:341).  Same argv contract ("pregraph -s cfg -o prefix
  *                                 [-K k -p P -a G -d D -R]"), same files written, same stderr counters, returns 0.
- *   pgb200_pregraph_main          the same with the 63-mer / 127-mer build flavour chosen at run time (the reference
- *                                 compiles two binaries with -DMER63 / -DMER127, Makefile:51-66).
+ *                                 The library's own call_pregraph has the 63-mer semantics; a SOAPdenovo-127mer build links
+ *                                 csrc/pregraph_shim.c (-DPGB_FLAVOUR127=1), which fixes the flavour at BUILD time like the
+ *                                 reference's -DMER63 / -DMER127 (Makefile:51-66) and keeps the `all` pipeline's globals.
+ *   pgb200_pregraph_main          the stage with the flavour as an argument (what the shim and the CLI front ends call).
+ *                                 PGB200_GPUS=n shards pass 1 over n GPUs of the box (see pgb200_xchg_* below).
  *   pgb200_feed_text + pgb200_finish_pass1 + pgb200_sweeps
  *                                 boolean prlRead2HashTable(char *libfile, char *outfile)   prlHashReads.c:304
  *                                 (readers readseq1by1.c:138-360, chopKmer4read :163-259, put_kmerset newhash.c:473-528,
@@ -22,8 +25,10 @@
  *   pgb200_output_vertex          void output_vertex(char *outfile)                   output_pregraph.c:50
  *   pgb200_destroy                void free_Sets(KmerSet **, int)                     newhash.c:601
  *
- * Threading: call from one host thread per engine; an engine owns one GPU stream; everything has completed on the
- * device when a call returns.  Not re-entrant per engine (the reference is not re-entrant at all).
+ * Threading: call from one host thread per engine (every entry point binds the calling thread to its engine's GPU); an engine
+ * owns its CUDA streams.  pgb200_feed_text returns when the chunk's text has been consumed (host buffers may be reused) while its
+ * kernels may still run; pgb200_finish_pass1 and every later phase call return with the device work completed.  Not re-entrant
+ * per engine (the reference is not re-entrant at all).
  */
 #ifndef PREGRAPH_B200_H
 #define PREGRAPH_B200_H

@@ -35,9 +35,6 @@ __device__ __forceinline__ void chop_read(const KParams<NW>& kp, const u64* __re
 }
 
 
-// tuple meta word: ordinal << 22 | position << 6 | left << 3 | right ; first-occurrence rank == meta >> 6
-PG_HD u64 tuple_meta(u64 ord, int j, unsigned left, unsigned right) { return (ord << 22) | ((u64)j << 6) | (left << 3) | right; }
-
 #if defined(__CUDACC__)
 // ---------------------------------------------------------------- TMA staging of a tile of packed reads
 // A block's 256 reads are one contiguous run of the read store (256 x W64 x 8 B, e.g. 10 KB at 150 bp): one elected thread

@@ -34,7 +34,6 @@ def test_127mer_flavour_is_fixed_at_link_time(tmp_path):
     cfg = synth.scenario_pe_fastq(str(tmp_path))
     ref, gpu = str(tmp_path / "ref"), str(tmp_path / "gpu")
     env = dict(os.environ)
-    env.pop("PGB200_FLAVOUR", None)
     for exe, out in ((util.REF127, ref), (B127, gpu)):
         r = subprocess.run([exe, "pregraph", "-s", cfg, "-K", "91", "-p", "4", "-a", "1", "-o", out], capture_output=True, text=True, env=env, timeout=600)
         assert r.returncode == 0, r.stderr[-3000:]
