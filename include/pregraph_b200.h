@@ -129,11 +129,14 @@ int pgb200_plan_files(const char *cfg, char *out, size_t cap);
 
 /* f2: binary edge sidecar `<prefix>.edge.b200` for a `contig` that links csrc/contig_sidecar.c -- the edges without
  * the gzip'ed text (the reference's loader: loadPreGraph.c:448-544).  Written by the stage when PGB200_EDGE_SIDECAR is set (the
- * byte-identical .edge.gz is still written).  This entry point converts edge TEXT (the uncompressed content of an .edge.gz) on the host:
+ * byte-identical .edge.gz is still written, unless the value is "only").  This entry point converts edge TEXT (the uncompressed content of an .edge.gz) on the host:
  *   48-byte header { char magic[8] = "PGB2EDGE"; u32 version = 1, K, kmer_words (2 | 4), 0; u64 n_records, num_ed, 0 }
  *   per record    { i32 length, cvg, bal_ed, seq_bytes = length / 4 + 1; u64 from[kmer_words], to[kmer_words]; u8 seq[seq_bytes] }
  *   (seq: 4 bases per byte, first base in bits 7:6, codes A0 C1 T2 G3 -- writeChar2tightString, seq.c:81)                         */
 int pgb200_edge_text_to_sidecar(const char *text, size_t nbytes, int K, int flavour127, uint64_t num_ed, const char *path);
+/* The way back, host only: `<prefix>.edge.b200` -> the byte-identical `<prefix>.edge.gz` (record text of output_pregraph.c:88-110, deflated
+ * like the stage does).  For pipelines that ran the stage with PGB200_EDGE_SIDECAR=only and want the .edge.gz later / in the background. */
+int pgb200_sidecar_to_edge_gz(const char *prefix);
 
 /* The drop-in stage entry points. */
 int pgb200_pregraph_main(int argc, char **argv, int flavour127);

@@ -22,7 +22,7 @@ EXPORTS = [
     "pgb200_xchg_setup", "pgb200_xchg_export", "pgb200_xchg_import", "pgb200_xchg_base", "pgb200_xchg_import_ptr", "pgb200_xchg_fence", "pgb200_flush", "pgb200_xchg_room", "pgb200_absorb",
     "pgb200_finish_pass1", "pgb200_reset_pass1", "pgb200_sweeps",
     "pgb200_build_layout", "pgb200_node_count", "pgb200_dump_nodes", "pgb200_remove_tips", "pgb200_kmer2edges",
-    "pgb200_read2edge", "pgb200_output_vertex", "pgb200_edge_text_to_sidecar", "pgb200_plan_files", "pgb200_pregraph_main", "call_pregraph",
+    "pgb200_read2edge", "pgb200_output_vertex", "pgb200_edge_text_to_sidecar", "pgb200_sidecar_to_edge_gz", "pgb200_plan_files", "pgb200_pregraph_main", "call_pregraph",
 ]
 
 
@@ -85,6 +85,7 @@ def load():
     for fn in ("pgb200_kmer2edges", "pgb200_read2edge", "pgb200_output_vertex"):
         getattr(lib, fn).argtypes = [C.c_void_p, C.c_char_p, C.POINTER(GraphStats)]
     lib.pgb200_edge_text_to_sidecar.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_uint64, C.c_char_p]
+    lib.pgb200_sidecar_to_edge_gz.argtypes = [C.c_char_p]
     lib.pgb200_plan_files.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
     lib.pgb200_pregraph_main.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int]
     _lib = lib
@@ -228,4 +229,11 @@ def edge_gz_to_sidecar(prefix: str, K: int, flavour127: int = 0):
     text = gzip.open(prefix + ".edge.gz", "rb").read()
     num_ed = int(open(prefix + ".preGraphBasic").read().split("EDGEs")[1].split()[0])
     if lib.pgb200_edge_text_to_sidecar(text, len(text), K, flavour127, num_ed, (prefix + ".edge.b200").encode()):
+        raise EngineError(lib.pgb200_last_error().decode())
+
+
+def sidecar_to_edge_gz(prefix: str):
+    """Host only: `<prefix>.edge.b200` -> the byte-identical `<prefix>.edge.gz`."""
+    lib = load()
+    if lib.pgb200_sidecar_to_edge_gz(prefix.encode()):
         raise EngineError(lib.pgb200_last_error().decode())

@@ -305,7 +305,7 @@ void EngineT<NW>::feed_text(const char* text, size_t nbytes, bool on_device, int
     // profiles/r02_e2e_flush_cadence.md).  PGB200_SKM=0|1 forces one of them.
     const bool use_skm = prm_.world > 1 || skm_mode_ > 0 || (skm_mode_ < 0 && on_device);
     cudaStream_t sd = use_skm ? st_dec_ : st_;   // the per-instance insert needs exact counters per chunk: one stream
-    const unsigned char* d_text;
+    const unsigned char* d_text = nullptr;
     const bool host_src = !on_device;
     if (host_src) {
         // H2D on its own stream into the buffer the previous chunk is NOT using: the copy overlaps the previous chunks' kernels

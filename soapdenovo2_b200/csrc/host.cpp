@@ -243,14 +243,73 @@ extern "C" int pgb200_edge_text_to_sidecar(const char* text, size_t nbytes, int 
     return 0;
 }
 
+// The way back: <prefix>.edge.b200 -> the byte-identical <prefix>.edge.gz (the sidecar holds every field of the text; the record
+// layout is output_pregraph.c:88-110: header line, then the bases 100 per line).  Host only; a pipeline that ran the stage with
+// PGB200_EDGE_SIDECAR=only can produce the .edge.gz later, or beside `contig`, with `pregraph-b200-<flavour> edgegz -g prefix`.
+extern "C" int pgb200_sidecar_to_edge_gz(const char* prefix) {
+    try {
+        const std::string in = std::string(prefix) + ".edge.b200";
+        FILE* f = fopen(in.c_str(), "rb");
+        if (!f) throw std::runtime_error("pgb200: cannot open " + in);
+        std::string raw;
+        char buf[1 << 16];
+        size_t got;
+        while ((got = fread(buf, 1, sizeof buf, f)) > 0) raw.append(buf, got);
+        fclose(f);
+        struct Hdr { char magic[8]; uint32_t version, K, kmer_words, r0; uint64_t n_records, num_ed, r1; } h;
+        if (raw.size() < sizeof h) throw std::runtime_error("pgb200: " + in + " is truncated");
+        memcpy(&h, raw.data(), sizeof h);
+        if (memcmp(h.magic, "PGB2EDGE", 8) != 0 || h.version != 1 || (h.kmer_words != 2 && h.kmer_words != 4)) throw std::runtime_error("pgb200: " + in + " is not an edge sidecar");
+        const int kw = (int)h.kmer_words;
+        std::string text;
+        text.reserve(raw.size() * 4 + (1 << 20));
+        size_t off = sizeof h;
+        for (uint64_t r = 0; r < h.n_records; r++) {
+            int32_t rec[4];
+            uint64_t km[8];
+            if (off + sizeof rec + (size_t)kw * 16 > raw.size()) throw std::runtime_error("pgb200: " + in + " is truncated");
+            memcpy(rec, raw.data() + off, sizeof rec); off += sizeof rec;
+            memcpy(km, raw.data() + off, (size_t)kw * 16); off += (size_t)kw * 16;
+            if (rec[0] < 0 || rec[3] != rec[0] / 4 + 1 || off + (size_t)rec[3] > raw.size()) throw std::runtime_error("pgb200: " + in + " is corrupt");
+            int n = snprintf(buf, sizeof buf, ">length %d,", rec[0]);
+            for (int side = 0; side < 2; side++) {
+                for (int w = 0; w < kw; w++) n += snprintf(buf + n, sizeof buf - n, w ? " %llx" : "%llx", (unsigned long long)km[side * kw + w]);
+                buf[n++] = ',';
+            }
+            n += snprintf(buf + n, sizeof buf - n, "cvg %d, %d\n", rec[1], rec[2]);
+            text.append(buf, (size_t)n);
+            const unsigned char* seq = reinterpret_cast<const unsigned char*>(raw.data() + off);
+            for (int i = 0; i < rec[0]; i++) {
+                text.push_back("ACTG"[(seq[i >> 2] >> (6 - 2 * (i & 3))) & 3]);
+                if ((i + 1) % 100 == 0) text.push_back('\n');
+            }
+            if (rec[0] % 100 != 0) text.push_back('\n');
+            off += (size_t)rec[3];
+        }
+        write_edge_gz(std::string(prefix) + ".edge.gz", text);
+    } catch (const std::exception& ex) {
+        g_err = ex.what();
+        return -1;
+    }
+    return 0;
+}
+
+// PGB200_EDGE_SIDECAR unset: <prefix>.edge.gz only (the reference's output).  Set: the sidecar first (a fraction of a second, so a
+// contig that links contig_sidecar.c never waits for the deflate), then the .edge.gz.  "only": the sidecar alone -- the deflate of
+// the edge text is sequential host work (its bytes must equal the reference's gz stream) and is the longest single item of a
+// full-size stage run, so a pipeline whose contig reads the sidecar can leave it out.
+static void write_edge_outputs(const std::string& prefix, const std::string& text, int K, int flavour127, uint64_t num_ed) {
+    const char* sc = getenv("PGB200_EDGE_SIDECAR");
+    if (sc && pgb200_edge_text_to_sidecar(text.data(), text.size(), K, flavour127, num_ed, (prefix + ".edge.b200").c_str())) throw std::runtime_error(g_err);
+    if (!(sc && !strcmp(sc, "only"))) write_edge_gz(prefix + ".edge.gz", text);
+}
+
 extern "C" int pgb200_kmer2edges(pgb200_engine* e, const char* prefix, pgb200_graph_stats* st) {
     PG_TRY
     EdgeStats es;
     std::string text;
     e->e->build_edges(&es, &text);
-    write_edge_gz(std::string(prefix) + ".edge.gz", text);
-    if (getenv("PGB200_EDGE_SIDECAR") && pgb200_edge_text_to_sidecar(text.data(), text.size(), e->prm.K, e->prm.flavour127, es.num_ed, (std::string(prefix) + ".edge.b200").c_str()))
-        throw std::runtime_error(g_err);
+    write_edge_outputs(prefix, text, e->prm.K, e->prm.flavour127, es.num_ed);
     fprintf(stderr, "%llu (%llu) edge(s) and %llu extra node(s) constructed.\n", (unsigned long long)es.num_ed, (unsigned long long)es.edges,
             (unsigned long long)es.extra_nodes);
     if (st) { st->num_ed = es.num_ed; st->edges = es.edges; st->extra_nodes = es.extra_nodes; }
@@ -403,6 +462,8 @@ static size_t last_record_start(const char* buf, size_t n, bool fastq) {
     }
 }
 
+static double now_s() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+
 // One pinned staging buffer; chunk i goes to engine i % G.  pgb200_feed_text returns when the chunk's H2D copy is done, its kernels
 // keep running, so with several GPUs the copy of chunk i+1 (to the next GPU) overlaps the kernels of chunk i.
 struct Feeder {
@@ -417,6 +478,7 @@ struct Feeder {
         fed_in_epoch = 0;
     }
     size_t fed_in_epoch = 0;
+    double s_read = 0, s_feed = 0;   // wall seconds inside fread / inside pgb200_feed_text (PGB200_VERBOSE)
     // streams one file; returns number of records
     uint64_t run(const std::string& fn, bool fastq, uint64_t ord_base, uint64_t ord_stride, int reverse, int maxlen) {
         fprintf(stderr, "Import reads from file:\n %s\n", fn.c_str());
@@ -432,7 +494,9 @@ struct Feeder {
         size_t have = 0;
         bool eof = false;
         while (!eof || have) {
+            const double t_r = now_s();
             size_t got = eof ? 0 : fread(pin + have, 1, cap - have, f);
+            s_read += now_s() - t_r;
             if (got == 0) eof = true;
             have += got;
             if (have == 0) break;
@@ -452,13 +516,18 @@ struct Feeder {
             pgb200_engine* eng = engs[next];
             if (engs.size() > 1) {
                 // several GPUs: room for this chunk's records in every arena region, and for its segment (128 per epoch over all GPUs)
-                const uint64_t upper = cut / (fastq ? 4 : 2) + 1;   // records <= lines / lines-per-record <= bytes / ...
+                // reads in this chunk, estimated generously from the library's read length (a record is a header, the bases and,
+                // for FASTQ, as many quality characters); an estimate that is too low is caught on the device (arena overflow error)
+                const uint64_t L = (uint64_t)std::max(8, maxlen);
+                const uint64_t upper = cut / (fastq ? L + 6 : L / 2 + 4) + 1;
                 if (fed_in_epoch + engs.size() > 120 || pgb200_xchg_room(eng, upper) != 1) collective_flush();
             }
+            const double t_f = now_s();
             if (pgb200_feed_text(eng, pin, cut, 0, fastq, ord_base + recs * ord_stride, ord_stride, reverse, maxlen)) {
                 fprintf(stderr, "readseqInLib return error! please make sure input file is correct fastq/fasta file \n(%s)\n", pgb200_last_error());
                 exit(-1);
             }
+            s_feed += now_s() - t_f;
             recs += pgb200_last_chunk_records(eng);
             next = (next + 1) % engs.size();
             fed_in_epoch++;
@@ -482,10 +551,23 @@ static void usage(int flavour127) {
     fprintf(stderr, "  -d <int>         KmerFreqCutoff: kmers with frequency no larger than KmerFreqCutoff will be deleted, [0]\n");
 }
 
-static double now_s() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+// PGB200_VERBOSE: where the stage's wall time went, in milliseconds (the reference's own "Time spent" lines are whole seconds)
+struct Timeline {
+    double t_prev;
+    std::string text;
+    explicit Timeline(double t) : t_prev(t) {}
+    void mark(const char* what) {
+        const double t = now_s();
+        char b[96];
+        snprintf(b, sizeof b, "%s%s %.0f ms", text.empty() ? "" : ", ", what, (t - t_prev) * 1e3);
+        text += b;
+        t_prev = t;
+    }
+};
 
 extern "C" int pgb200_pregraph_main(int argc, char** argv, int flavour127) {
     double t_all = now_s();
+    Timeline tl(t_all);
     fprintf(stderr, "\n********************\nPregraph\n********************\n\n");
     // ---- initenv (pregraph.c:142-220)
     pgb200_params prm;
@@ -557,6 +639,7 @@ extern "C" int pgb200_pregraph_main(int argc, char** argv, int flavour127) {
         fprintf(stderr, "[pgb200] pass 1 sharded over %d GPUs (minimizer-bucket ranges, records stored peer to peer)\n", n_gpus);
     }
     fprintf(stderr, "%d thread(s) initialized.\n", prm.P);
+    tl.mark("engines");
     uint64_t ord_next = 0, n_reads = 0;
     {
         Feeder fd;
@@ -577,6 +660,7 @@ extern "C" int pgb200_pregraph_main(int argc, char** argv, int flavour127) {
             }
         }
         if (n_gpus > 1) fd.collective_flush();
+        if (prm.verbose) fprintf(stderr, "[pgb200] reading the files: %.0f ms in fread, %.0f ms in feed_text (H2D copy + launches)\n", fd.s_read * 1e3, fd.s_feed * 1e3);
     }
     pgb200_pass1_stats p1;
     memset(&p1, 0, sizeof p1);
@@ -587,6 +671,7 @@ extern "C" int pgb200_pregraph_main(int argc, char** argv, int flavour127) {
         p1.ms_decode = std::max(p1.ms_decode, q.ms_decode); p1.ms_insert = std::max(p1.ms_insert, q.ms_insert);
     }
     double t1 = now_s();
+    tl.mark("reads -> k-mer table");
     fprintf(stderr, "Time spent on hashing reads: %ds, %lld read(s) processed.\n", (int)(t1 - t0), (long long)n_reads);
     fprintf(stderr, "%lli node(s) allocated, %lli kmer(s) in reads, %lli kmer(s) processed.\n", (long long)p1.distinct, (long long)p1.instances, (long long)p1.instances);
     fprintf(stderr, "[pgb200] pass 1: %.3f s wall, decode %.1f ms + insert %.1f ms on the GPU%s, table %llu slots\n", t1 - t0, p1.ms_decode, p1.ms_insert,
@@ -602,6 +687,7 @@ extern "C" int pgb200_pregraph_main(int argc, char** argv, int flavour127) {
         for (int i = 0; i < 256; i++) hist[i] += h1[i];
         lin += l1; rem += r1;
     }
+    tl.mark("sweeps");
     if ((signed char)prm.D) fprintf(stderr, "%llu kmer(s) removed.\n", (unsigned long long)rem);
     fprintf(stderr, "%llu linear node(s) marked.\n", (unsigned long long)lin);
     // The graph phases walk across buckets: the shards (tables with their swept flags, packed reads) are folded into GPU 0, which
@@ -611,6 +697,7 @@ extern "C" int pgb200_pregraph_main(int argc, char** argv, int flavour127) {
         pgb200_destroy(engs[g]);
         engs[g] = nullptr;
     }
+    if (n_gpus > 1) tl.mark("gather shards");
     {
         std::string s;
         char b[32];
@@ -618,7 +705,7 @@ extern "C" int pgb200_pregraph_main(int argc, char** argv, int flavour127) {
         try { write_file(prefix + ".kmerFreq", s.data(), s.size()); } catch (const std::exception& ex) { fprintf(stderr, "%s\n", ex.what()); exit(-1); }
     }
     fprintf(stderr, "Time spent on pre-graph construction: %ds.\n\n", (int)(now_s() - t0));
-    if (getenv("PGB200_PASS1_ONLY")) { pgb200_destroy(eng); return 0; }
+    if (getenv("PGB200_PASS1_ONLY")) { for (auto* e : engs) pgb200_destroy(e); return 0; }
 
     // ---- layout + tips (removeSingleTips / removeMinorTips)
     t0 = now_s();
@@ -626,6 +713,7 @@ extern "C" int pgb200_pregraph_main(int argc, char** argv, int flavour127) {
     pgb200_graph_stats gs;
     memset(&gs, 0, sizeof gs);
     if (pgb200_remove_tips(eng, &gs)) die("tips");
+    tl.mark("layout + tips");
     fprintf(stderr, "Time spent on removing tips: %ds.\n\n", (int)(now_s() - t0));
     // ---- edges (kmer2edges)
     t0 = now_s();
@@ -642,22 +730,24 @@ extern "C" int pgb200_pregraph_main(int argc, char** argv, int flavour127) {
         const uint64_t ne = es.num_ed;
         gz_thread = std::thread([&, ne]() {
             try {
-                // the binary sidecar first (a fraction of a second): a contig that links contig_sidecar.c never waits for the gzip
-                if (getenv("PGB200_EDGE_SIDECAR") && pgb200_edge_text_to_sidecar(edge_text.data(), edge_text.size(), prm.K, flavour127, ne, (prefix + ".edge.b200").c_str()))
-                    throw std::runtime_error(pgb200_last_error());
-                write_edge_gz(prefix + ".edge.gz", edge_text);
+                write_edge_outputs(prefix, edge_text, prm.K, flavour127, ne);
             } catch (const std::exception& ex) { gz_error = ex.what(); }
         });
     } catch (const std::exception& ex) { fprintf(stderr, "pgb200: edges failed: %s\n", ex.what()); exit(-1); }
+    tl.mark("edges");
     fprintf(stderr, "Time spent on constructing edges: %ds.\n\n", (int)(now_s() - t0));
     // ---- pass 2 (prlRead2edge)
     t0 = now_s();
     if (pgb200_read2edge(eng, prefix.c_str(), &gs)) { if (gz_thread.joinable()) gz_thread.join(); die("pass 2"); }
     fprintf(stderr, "Time spent on aligning reads: %ds.\n\n", (int)(now_s() - t0));
+    tl.mark("pass 2 + its files");
     gz_thread.join();
+    tl.mark("waiting for the edge file");
     if (!gz_error.empty()) { fprintf(stderr, "%s\n", gz_error.c_str()); exit(-1); }
     if (pgb200_output_vertex(eng, prefix.c_str(), &gs)) die("vertex output");
     pgb200_destroy(eng);
+    tl.mark("vertex + teardown");
+    if (prm.verbose) fprintf(stderr, "[pgb200] stage wall %.2f s: %s\n", now_s() - t_all, tl.text.c_str());
     fprintf(stderr, "Overall time spent on constructing pre-graph: %dm.\n\n", (int)(now_s() - t_all) / 60);
     return 0;
 }

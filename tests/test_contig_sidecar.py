@@ -55,9 +55,15 @@ def test_contig_reads_the_sidecar(tmp_path, flav, K, extra):
     os.remove(side_run + ".edge.gz")
     util.run([b200_bin, "contig", "-g", side_run, *extra])
     util.compare(ref, side_run, OUT)
+    # and the way back: the sidecar regenerates the reference's .edge.gz byte for byte (text AND deflate stream)
+    api.sidecar_to_edge_gz(side_run)
+    util.compare(ref, side_run, ["edge.gz"])
 
 
 def test_sidecar_converter_rejects_garbage(tmp_path):
     lib = api.load()
     bad = b">length 5,1 2,3 4,cvg x, 1\nACGTA\n"
     assert lib.pgb200_edge_text_to_sidecar(bad, len(bad), 31, 0, 2, str(tmp_path / "x.b200").encode()) != 0
+    open(str(tmp_path / "y.edge.b200"), "wb").write(b"PGB2EDGE" + bytes(20))
+    assert lib.pgb200_sidecar_to_edge_gz(str(tmp_path / "y").encode()) != 0
+    assert lib.pgb200_sidecar_to_edge_gz(str(tmp_path / "absent").encode()) != 0

@@ -73,3 +73,11 @@ def test_stage_writes_the_edge_sidecar_and_contig_reads_it(tmp_path):
     util.run([util.REF63, "contig", "-g", ref, "-R"])
     util.run([B63, "contig", "-g", gpu, "-R"])
     util.compare(ref, gpu, ["contig", "Arc", "updated.edge", "ContigIndex"])
+    # "only": the sidecar without the (sequential, slow) deflate of the edge text; everything else unchanged
+    only = str(tmp_path / "only")
+    r = subprocess.run([B63, "pregraph", "-s", cfg, "-K", "63", "-p", "8", "-a", "1", "-R", "-o", only], capture_output=True, text=True,
+                       env=dict(os.environ, PGB200_EDGE_SIDECAR="only"), timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert not os.path.exists(only + ".edge.gz")
+    assert open(only + ".edge.b200", "rb").read() == side
+    util.compare(ref, only, [x for x in util.SUFFIXES_R if x != "edge.gz"])
