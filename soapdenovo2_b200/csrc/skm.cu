@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(SKM_PART_THREADS) k_skm_rescan(SkmSendArgs a, 
 
 // ------------------------------------------------------------------------------------------------ aggregation
 // Shared-memory table of one bucket, structure of arrays: key words [NW][S], payload [S], rank [S], claim list [S] (u16).
-// Claim protocol: CAS(key0, EMPTY -> w0|BUSY), write the other key words + the first instance's payload and rank, fence, store w0.
+// Claim protocol: CAS(key0, EMPTY -> w0|BUSY), write the other key words, fence, store w0.  Empty slots hold {PAYLOAD_FRESH, ~0} in
+// their payload / rank words, so the claimer records its own instance together with the lanes that found the key (one update path).
 // A thread that meets a BUSY key0 whose other bits match waits for the publication (independent thread scheduling: the claimer makes
 // progress even inside the same warp).  The claimer also appends the slot to the claim list (the flush walks the list, not the
 // table).  (Prefetching the k-mer's home slot of the GLOBAL table into L2 at claim time measured no difference and was dropped.)
@@ -223,12 +224,10 @@ struct SmemTable {
     // finds or claims its slot (lanes differ only in the number of probes), then the lanes that found an existing key apply their
     // instance TOGETHER (without the barrier the lanes that match on their first probe run the long update on their own while the
     // others keep probing: the update code then executes several times per step with a few active lanes each).
-    // find(): 1 = key present at idx, 2 = claimed by this lane (first instance already recorded), 3 = no room (caller spills)
-    __device__ __forceinline__ int find(const Table<NW>& tab, const Kmer<NW>& k, unsigned left, unsigned right, u64 rank, u32& idx) const {
+    // find(): 1 = key present at idx (found, or claimed by this lane just now), 3 = no room (caller spills)
+    __device__ __forceinline__ int find(const Table<NW>& tab, const Kmer<NW>& k, u32& idx) const {
         idx = (u32)(((u64)skm_slot_hash(k, 32) * (u64)S) >> 32);
         volatile u64* vkey = key;
-        volatile u64* vpay = pay;
-        volatile u64* vrnk = rnk;
         for (int probe = 0; probe < S; probe++) {
             u64 k0 = vkey[idx];
             if (k0 == EMPTY64) {
@@ -237,13 +236,11 @@ struct SmemTable {
                 if (old == EMPTY64) {
 #pragma unroll
                     for (int w = 1; w < NW; w++) vkey[w * S + idx] = k.w[w];
-                    vpay[idx] = payload_apply(PAYLOAD_FRESH, left, right);
-                    vrnk[idx] = rank;
                     __threadfence_block();
                     vkey[idx] = k.w[0];
                     const u32 n = atomicAdd(count, 1u);
                     list[n] = (LT)idx;
-                    return 2;
+                    return 1;   // an empty slot holds {PAYLOAD_FRESH, ~0}: the claimer records its instance with everybody else in apply()
                 }
                 k0 = old;
             }
@@ -372,7 +369,11 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS, SKM_APPLY_MIN_BLOCKS(NW)) k
     SmemTable<NW, SKM_SLOTS, SKM_SOFT_LIMIT, unsigned short> st{s_dyn, s_dyn + NW * SKM_SLOTS, s_dyn + (NW + 1) * SKM_SLOTS, reinterpret_cast<unsigned short*>(s_dyn + (NW + 2) * SKM_SLOTS), &s_count};
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned lane_le = 0xffffffffu >> (31 - lane);
-    for (int i = tid; i < SKM_SLOTS; i += SKM_APPLY_THREADS) st.key[i] = EMPTY64;   // the flush re-empties what it merges
+    for (int i = tid; i < SKM_SLOTS; i += SKM_APPLY_THREADS) {   // the flush re-empties what it merges
+        st.key[i] = EMPTY64;
+        st.pay[i] = PAYLOAD_FRESH;
+        st.rnk[i] = ~0ull;
+    }
     if (tid == 0) { s_tot_new = 0; s_tot_spill = 0; }
     const int n_segs = (int)a.segs->n;
     const u32* my_so = tid < n_segs ? a.segs->segoff[tid] : nullptr;
@@ -450,9 +451,13 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS, SKM_APPLY_MIN_BLOCKS(NW)) k
         u64 nh = 0, nx[NW + 1];
 #pragma unroll
         for (int i = 0; i < NW + 1; i++) nx[i] = 0;
+        // batch size: the bucket's records are split evenly over a multiple of WARPS batches (R = 210 records on 8 warps: 8 batches of
+        // 27, not 6 of 32 + 1 of 18 + an idle warp), so the warps reach the barrier before the flush together
+        const u32 n_batches = (u32)WARPS * ((R + 32u * WARPS - 1) / (32u * WARPS));
+        const u32 bsz = (R + n_batches - 1) / n_batches;   // <= 32
         auto load_rec = [&](u32 q) {
             nh = 0;
-            if (q < R) {
+            if (q < R && lane < (int)bsz) {
                 int lo = 0, hi = n_segs;
                 while (hi - lo > 1) {
                     const int mid = (lo + hi) >> 1;
@@ -473,24 +478,24 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS, SKM_APPLY_MIN_BLOCKS(NW)) k
         };
         // batches are handed out dynamically (the first WARPS ones are pre-assigned): a warp that draws short runs takes more of them,
         // so the warps reach the barrier before the flush together
-        load_rec((u32)wid * 32u + lane);
+        load_rec((u32)wid * bsz + lane);
         u32 nb = 0x7FFFFFFu;                                  // (a warp without a first batch must not draw one; x 32 still fits)
-        if ((u32)wid * 32u < R) {
+        if ((u32)wid * bsz < R) {
             if (lane == 0) nb = atomicAdd(&s_batch, 1u);
             nb = __shfl_sync(0xffffffffu, nb, 0);
         }
-        for (u32 rb = (u32)wid * 32u; rb < R;) {
+        for (u32 rb = (u32)wid * bsz; rb < R;) {
             const u64 hdr = nh;
             u64 x[NW + 1];
 #pragma unroll
             for (int i = 0; i < NW + 1; i++) x[i] = nx[i];
-            const u32 rb_next = nb * 32u;
+            const u32 rb_next = nb * bsz;
             load_rec(rb_next + lane);                         // the next batch is in flight while this one is processed
             if (rb_next < R) {
                 if (lane == 0) nb = atomicAdd(&s_batch, 1u);
                 nb = __shfl_sync(0xffffffffu, nb, 0);
             }
-            const bool valid = rb + lane < R;
+            const bool valid = rb + lane < R && lane < (int)bsz;
             const u32 n = valid ? (u32)skm_rec_n(hdr) : 0u;
             u32 inc = n;
 #pragma unroll
@@ -517,7 +522,7 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS, SKM_APPLY_MIN_BLOCKS(NW)) k
                     const SkmInst<NW> in = skm_instance_rec<NW>(kp, h, y, t);
                     const u64 rank = skm_rec_rank(h, t);
                     u32 slot;
-                    const int state = st.find(tab, in.canon, in.left, in.right, rank, slot);
+                    const int state = st.find(tab, in.canon, slot);
                     __syncwarp(has_mask);   // the lanes re-join before the counter update (see SmemTable)
                     if (state == 1) st.apply(slot, in.left, in.right, rank);
                     else if (state == 3) {
@@ -540,6 +545,8 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS, SKM_APPLY_MIN_BLOCKS(NW)) k
             for (int w = 0; w < NW; w++) k.w[w] = st.key[w * SKM_SLOTS + idx];
             my_new += table_merge(tab, k, st.pay[idx], st.rnk[idx]);
             st.key[idx] = EMPTY64;
+            st.pay[idx] = PAYLOAD_FRESH;
+            st.rnk[idx] = ~0ull;
         }
         if (my_new) atomicAdd(&s_new, my_new);
         tot_new += my_new;
