@@ -148,7 +148,6 @@ __global__ void __launch_bounds__(128) k_edge_walk(Table<NW> tab, KParams<NW> kp
         unsigned c = kfirst(end.second_last, kp);
         u64 rid = T->aux * 8 + (end.sm ? 4u + c : (c ^ 2u));      // dislink2prevUncertain(last, firstCh(second_last), last.sm)
         if (!(T->payload & PL_DELETED)) r.rev_id = rid;
-        int bal = rid == sid ? 0 : 1;
         u32 cvg = edge_cvg(sv.symbol, end.length);
         // ">length %d,%llx %llx,%llx %llx,cvg %d, %d\n"
         r.hdr_len = 8 + dec_len(end.length) + 1 + kmer_hex_len(end.frm, out_words) + 1 + kmer_hex_len(end.to, out_words) + 1 + 4 + dec_len(cvg) + 2 + 1 + 1;

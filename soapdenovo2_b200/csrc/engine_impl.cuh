@@ -103,6 +103,9 @@ public:
     DevBuf text_bufs_[2], line_buf_, scan_buf_, hist_buf_;
     int text_flip_ = 0;
     cudaStream_t st_copy_ = nullptr;   // H2D of chunk i+1 overlaps the insert of chunk i
+    cudaStream_t st_clear_ = nullptr;  // the table clear between two passes (reset_pass1)
+    cudaEvent_t ev_clear_ = nullptr;
+    bool clear_pending_ = false;
     cudaEvent_t ev_copy_ = nullptr;
     void settle_timing();                        // waits for every fed chunk's kernels and books their times
     void settle_oldest();
@@ -179,6 +182,14 @@ public:
     void sync() {
         if (st_dec_) PG_CUDA(cudaStreamSynchronize(st_dec_));
         PG_CUDA(cudaStreamSynchronize(st_));
+        if (clear_pending_) { PG_CUDA(cudaStreamSynchronize(st_clear_)); clear_pending_ = false; }
+    }
+    // reset_pass1 clears the table on its own stream: the next pass's decode and partition kernels (which do not touch the table) run
+    // beside the 17 GB memset instead of behind it.  Whoever touches the table next orders the insert stream behind the clear.
+    void join_table_clear() {
+        if (!clear_pending_) return;
+        PG_CUDA(cudaStreamWaitEvent(st_, ev_clear_, 0));
+        clear_pending_ = false;
     }
     void read_counters() {   // everything queued so far has completed when this returns
         if (st_dec_) PG_CUDA(cudaStreamSynchronize(st_dec_));

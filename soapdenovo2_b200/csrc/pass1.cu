@@ -135,6 +135,7 @@ void EngineT<NW>::grow_table(u64 new_cap) {
 
 template <int NW>
 void EngineT<NW>::create_table_if_needed() {
+    join_table_clear();
     if (tab_.slots) return;
     u64 want = prm_.table_slots;
     if (!want) {
@@ -222,6 +223,7 @@ void EngineT<NW>::absorb(IEngine* other_i) {
     PG_CUDA(cudaSetDevice(o->prm_.device));
     o->settle_timing();
     o->read_counters();
+    o->sync();   // (also a table clear nobody joined)
     PG_CUDA(cudaSetDevice(prm_.device));
     int can = 0;
     PG_CUDA(cudaDeviceCanAccessPeer(&can, prm_.device, o->prm_.device));
@@ -274,9 +276,13 @@ void EngineT<NW>::reset_pass1() {
     order_buf_.release();
     n_nodes_ = 0;
     sync();
-    // the table is cleared on the insert stream WITHOUT waiting: the next pass starts with decoding (another stream), and whatever
-    // touches the table next is ordered behind this memset by the stream
-    if (tab_.slots) PG_CUDA(cudaMemsetAsync(tab_buf_.p, 0xFF, cap_ * sizeof(Slot<NW>), st_));
+    // the table is cleared on its own stream WITHOUT waiting: the next pass starts with decoding and partitioning, which do not touch
+    // the table; whatever touches it next joins the clear first (create_table_if_needed -> join_table_clear)
+    if (tab_.slots) {
+        PG_CUDA(cudaMemsetAsync(tab_buf_.p, 0xFF, cap_ * sizeof(Slot<NW>), st_clear_));
+        PG_CUDA(cudaEventRecord(ev_clear_, st_clear_));
+        clear_pending_ = true;
+    }
     for (int i = 0; i < C_COUNT; i++) h_cnt_[i] = 0;
     if (prm_.verbose >= 2) fprintf(stderr, "[pgb200] reset_pass1: %.2f ms host\n", host_now() - t0);
 }
@@ -284,6 +290,23 @@ void EngineT<NW>::reset_pass1() {
 // ------------------------------------------------------------------------------------------------ K4: sweeps
 // delow (thread_delow): zero every link counter <= D, deleted=1 if nothing is left.  mark (thread_mark): linear=1 iff exactly
 // one non-zero left and one non-zero right link (NO deleted check there); histogram of cov.  All per-entry => one pass.
+// The table is streamed once: K <= 63 slots arrive with one 256-bit load each (key + payload in one 32 B sector), two slots per
+// thread in flight; the payload is written back only when a flag or a counter changed.
+template <int NW>
+__device__ __forceinline__ u64 sweep_payload(u64 p, int D, unsigned& rem, unsigned& lin, unsigned* s_hist) {
+    if (D > 0) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            unsigned l = pl_l(p, c), r = pl_r(p, c);
+            if (l > 0 && l <= (unsigned)D) p = pl_clear_l(p, c);
+            if (r > 0 && r <= (unsigned)D) p = pl_clear_r(p, c);
+        }
+        if ((p & PL_LLINKS_MASK) == 0 && (p & PL_RLINKS_MASK) == 0) { p |= PL_DELETED; rem++; }
+    }
+    atomicAdd(&s_hist[pl_cov(p)], 1u);
+    if (pl_nl(p) == 1 && pl_nr(p) == 1) { p |= PL_LINEAR; lin++; }
+    return p;
+}
 template <int NW>
 __global__ void __launch_bounds__(256) k_sweep(Table<NW> tab, int D, u64* hist, u64* counters) {
     __shared__ unsigned s_hist[256];
@@ -291,24 +314,33 @@ __global__ void __launch_bounds__(256) k_sweep(Table<NW> tab, int D, u64* hist, 
     s_hist[threadIdx.x] = 0;
     if (threadIdx.x == 0) { s_lin = 0; s_rem = 0; }
     __syncthreads();
-    u64 n = tab.mask + 1;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
-        Slot<NW>* s = tab.slots + i;
-        if (!slot_occupied(s)) continue;
-        u64 p = s->payload;
-        if (D > 0) {
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                unsigned l = pl_l(p, c), r = pl_r(p, c);
-                if (l > 0 && l <= (unsigned)D) p = pl_clear_l(p, c);
-                if (r > 0 && r <= (unsigned)D) p = pl_clear_r(p, c);
-            }
-            if ((p & PL_LLINKS_MASK) == 0 && (p & PL_RLINKS_MASK) == 0) { p |= PL_DELETED; atomicAdd(&s_rem, 1u); }
+    const u64 n = tab.mask + 1, stride = (u64)gridDim.x * blockDim.x;
+    unsigned rem = 0, lin = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
+        Slot<NW>* s0 = tab.slots + i;
+        Slot<NW>* s1 = tab.slots + (i + stride < n ? i + stride : i);
+        const bool two = i + stride < n;
+        u64 k0a, k0b, p0, k1a, k1b, p1;
+        if constexpr (NW == 2) {
+            const U256 v0 = ld256(s0), v1 = ld256(s1);
+            k0a = v0.a; k0b = v0.b; p0 = v0.c;
+            k1a = v1.a; k1b = v1.b; p1 = v1.c;
+        } else {
+            const U128 a0 = ldcg128(s0->key), a1 = ldcg128(s1->key);
+            k0a = a0.a; k0b = a0.b; k1a = a1.a; k1b = a1.b;
+            p0 = ldcg64(&s0->payload); p1 = ldcg64(&s1->payload);
         }
-        atomicAdd(&s_hist[pl_cov(p)], 1u);
-        if (pl_nl(p) == 1 && pl_nr(p) == 1) { p |= PL_LINEAR; atomicAdd(&s_lin, 1u); }
-        s->payload = p;
+        if (!(k0a == EMPTY64 && k0b == EMPTY64)) {
+            const u64 q = sweep_payload<NW>(p0, D, rem, lin, s_hist);
+            if (q != p0) s0->payload = q;
+        }
+        if (two && !(k1a == EMPTY64 && k1b == EMPTY64)) {
+            const u64 q = sweep_payload<NW>(p1, D, rem, lin, s_hist);
+            if (q != p1) s1->payload = q;
+        }
     }
+    if (lin) atomicAdd(&s_lin, lin);
+    if (rem) atomicAdd(&s_rem, rem);
     __syncthreads();
     if (s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (u64)s_hist[threadIdx.x]);
     if (threadIdx.x == 0) {
@@ -347,6 +379,8 @@ EngineT<NW>::EngineT(const PgParams& p) : prm_(p) {
     kp_ = make_kparams<NW>(p.K);
     PG_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     PG_CUDA(cudaStreamCreateWithFlags(&st_copy_, cudaStreamNonBlocking));
+    PG_CUDA(cudaStreamCreateWithFlags(&st_clear_, cudaStreamNonBlocking));
+    PG_CUDA(cudaEventCreateWithFlags(&ev_clear_, cudaEventDisableTiming));
     PG_CUDA(cudaStreamCreateWithFlags(&st_dec_, cudaStreamNonBlocking));
     PG_CUDA(cudaEventCreateWithFlags(&ev_dec_done_, cudaEventDisableTiming));
     PG_CUDA(cudaEventCreate(&ev_flush_));
@@ -376,6 +410,8 @@ EngineT<NW>::~EngineT() {
     if (st_dec_) { cudaStreamSynchronize(st_dec_); cudaStreamDestroy(st_dec_); }
     if (ev_copy_) cudaEventDestroy(ev_copy_);
     if (st_copy_) cudaStreamDestroy(st_copy_);
+    if (st_clear_) { cudaStreamSynchronize(st_clear_); cudaStreamDestroy(st_clear_); }
+    if (ev_clear_) cudaEventDestroy(ev_clear_);
     if (st_) cudaStreamDestroy(st_);
 }
 

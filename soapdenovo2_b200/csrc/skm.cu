@@ -49,7 +49,7 @@ struct CountEmit {
 
 __global__ void __launch_bounds__(SKM_PART_THREADS) k_skm_count(SkmGeom g, const u64* __restrict__ words, const u32* __restrict__ lens, u64 n_rec, int W64,
                                                                u32* cnt, u32* side, u8* nruns) {
-    extern __shared__ u32 s_ring[];   // [2 * g.w][blockDim.x]: one column per thread, bank = thread -> conflict-free
+    extern __shared__ u32 s_ring[];   // [g.w][blockDim.x]: one column per thread, bank = thread -> conflict-free
     for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += (u64)gridDim.x * blockDim.x) {
         CountEmit e{cnt, side + r * SKM_SIDE_RUNS, 0};
         skm_scan_read(g, words + r * (u64)W64, (int)lens[r], s_ring + threadIdx.x, (int)blockDim.x, e);
@@ -603,8 +603,8 @@ void EngineT<NW>::skm_init() {
     PG_CUDA(cudaMemsetAsync(skm_misc_.p, 0, skm_misc_.bytes, st_));
     for (auto& e : ev_skm_) PG_CUDA(cudaEventCreate(&e));
     skm_part_threads_ = SKM_PART_THREADS;
-    while ((size_t)skm_part_threads_ * 2 * skm_geom_.w * sizeof(u32) > 160 * 1024 && skm_part_threads_ > 32) skm_part_threads_ /= 2;
-    const size_t ring = (size_t)skm_part_threads_ * 2 * skm_geom_.w * sizeof(u32);
+    while ((size_t)skm_part_threads_ * skm_geom_.w * sizeof(u32) > 160 * 1024 && skm_part_threads_ > 32) skm_part_threads_ /= 2;
+    const size_t ring = (size_t)skm_part_threads_ * skm_geom_.w * sizeof(u32);
     if (ring > 48 * 1024) {
         PG_CUDA(cudaFuncSetAttribute(k_skm_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
         PG_CUDA(cudaFuncSetAttribute(k_skm_rescan<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
@@ -781,7 +781,7 @@ void EngineT<NW>::skm_feed_chunk(size_t ci) {
     const int world = xa_geom_.world;
     PG_CUDA(cudaMemsetAsync(skm_cnt_.p, 0, (B + 1) * sizeof(u32), st_));
     PG_CUDA(cudaMemsetAsync(skm_cursor_.p, 0, (B + 1) * sizeof(u32), st_));
-    const size_t ring = (size_t)skm_part_threads_ * 2 * skm_geom_.w * sizeof(u32);
+    const size_t ring = (size_t)skm_part_threads_ * skm_geom_.w * sizeof(u32);
     const unsigned blocks = (unsigned)std::min<u64>((ch.n_rec + skm_part_threads_ - 1) / skm_part_threads_, 148ull * 16);
     skm_side_.ensure(ch.n_rec * (SKM_SIDE_RUNS * sizeof(u32) + 1) + 256);
     u32* side = skm_side_.template as<u32>();

@@ -71,9 +71,11 @@ PG_HD u32 skm_side_bucket(u32 e) { return e & ((1u << SKM_MAX_BUCKET_BITS) - 1u)
 PG_HD int skm_side_n(u32 e) { return (int)((e >> SKM_MAX_BUCKET_BITS) & 31u) + 1; }
 PG_HD bool skm_side_last(u32 e) { return (e >> 31) != 0; }
 
-// Split one read into runs.  scratch[slot * stride] (slot < 2 * g.w) holds, per thread, the order values of the current block of w
-// m-mer positions and the suffix minima of the previous block: the minimum of a window of w positions is
-// min(suffix minimum of the previous block, running minimum of the current block)  (van Herk / Gil-Werman).  All threads of a warp
+// Split one read into runs.  scratch[slot * stride] (slot < g.w) holds, per thread, the suffix minima of the previous block of w
+// m-mer positions, overwritten from the front by the order values of the block being filled (slot o is written at offset o, the
+// suffix minimum read at offset o is slot o + 1; the backward pass at the end of a block turns the values into suffix minima in
+// place): the minimum of a window of w positions is min(suffix minimum of the previous block, running minimum of the current
+// block)  (van Herk / Gil-Werman).  All threads of a warp
 // are at the same position of their reads, so the once-per-block backward pass is not divergent (a per-lane rescan whenever the
 // minimum leaves the window would be: some lane rescans at almost every step).  The bucket hash is only evaluated when the
 // minimum changes (a few times per read).
@@ -82,8 +84,8 @@ template <class Emit>
 PG_HD void skm_scan_read(const SkmGeom& g, const u64* wp, int L, u32* scratch, int stride, Emit& emit) {
     const int K = g.K, m = g.m, w = g.w;
     if (L < K + 1) return;   // reads shorter than K+1 contribute nothing (prlHashReads.c:504,642)
-    u32* cur_blk = scratch;                 // raw order values of the block being filled
-    u32* suf_blk = scratch + w * stride;    // suffix minima of the previous block
+    u32* cur_blk = scratch;                 // raw order values of the block being filled (slots 0 .. o)
+    u32* suf_blk = scratch;                 // suffix minima of the previous block (slots o + 1 .. w - 1)
     u32 fm = 0, rm = 0, pref = 0xFFFFFFFFu;
     int o = 0;                              // offset of m-mer position p inside its block
     u32* cur_p = cur_blk;                   // = cur_blk + o * stride
@@ -129,10 +131,9 @@ PG_HD void skm_scan_read(const SkmGeom& g, const u64* wp, int L, u32* scratch, i
         suf_p += stride;
         if (++o == w) {                     // block complete: its suffix minima serve the next w-1 windows
             u32 run = 0xFFFFFFFFu;
-            const u32* src = cur_blk + (w - 1) * stride;
-            u32* dst = suf_blk + (w - 1) * stride;
-            for (int q = w - 1; q >= 0; q--, src -= stride, dst -= stride) {
-                const u32 v = *src;
+            u32* dst = cur_blk + (w - 1) * stride;
+            for (int q = w - 1; q >= 0; q--, dst -= stride) {
+                const u32 v = *dst;
                 run = v < run ? v : run;
                 *dst = run;
             }

@@ -102,22 +102,6 @@ PG_D U256 ld256(const void* p) {
     asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p) : "memory");
     return r;
 }
-// Predicated forms (one basic block, no data-dependent branch around the memory instruction): used by the per-lane state
-// machine of k_chop_insert_sm2 so that the loads and both kinds of CAS of one warp are ISSUED back to back and their
-// latencies overlap.  `old` / `v` keep their value when the predicate is false.
-PG_D void ld256_if(bool p, const void* a, U256& v) {
-    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %5, 0;\n @p ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];\n}"
-                 : "+l"(v.a), "+l"(v.b), "+l"(v.c), "+l"(v.d) : "l"(a), "r"((unsigned)p) : "memory");
-}
-PG_D void cas64_if(bool p, u64* a, u64 cmp, u64 val, u64& old) {
-    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %4, 0;\n @p atom.relaxed.gpu.global.cas.b64 %0, [%1], %2, %3;\n}"
-                 : "+l"(old) : "l"(a), "l"(cmp), "l"(val), "r"((unsigned)p) : "memory");
-}
-PG_D void cas128_if(bool p, void* a, U128 cmp, U128 val, U128& old) {
-    asm volatile("{\n .reg .pred p;\n .reg .b128 c, v, o;\n setp.ne.u32 p, %7, 0;\n mov.b128 c, {%3,%4};\n mov.b128 v, {%5,%6};\n"
-                 " mov.b128 o, {%0,%1};\n @p atom.relaxed.gpu.global.cas.b128 o, [%2], c, v;\n mov.b128 {%0,%1}, o;\n}"
-                 : "+l"(old.a), "+l"(old.b) : "l"(a), "l"(cmp.a), "l"(cmp.b), "l"(val.a), "l"(val.b), "r"((unsigned)p) : "memory");
-}
 PG_D u64 ldcg64(const void* p) {
     u64 r;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");

@@ -55,7 +55,7 @@ static int run_case(int K, int n_reads, int maxlen, u32 n_buckets, bool low_comp
     KParams<NW> kp = make_kparams<NW>(K);
     SkmGeom g = make_skm_geom(K, n_buckets);
     const int W64 = (maxlen + 31) / 32;
-    std::vector<u32> ring(2 * g.w);
+    std::vector<u32> ring(g.w);
     typedef std::map<Kmer<NW>, Agg, KeyLess<NW>> Map;
     Map direct, half[2], merged;
     std::map<u32, u64> bucket_load;
