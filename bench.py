@@ -334,19 +334,30 @@ def main():
         per_rec = 15.0 if K <= 63 else 9.0
         xchg = pdist.RecordExchange(eng, dist, cap_records=int(float(os.environ.get("PGB200_BENCH_ARENA_FACTOR", "1.4")) * total_instances / per_rec / world) + (1 << 20))
 
+    timeline = [0.0] * 5 if os.environ.get("PGB200_BENCH_TIMELINE") else None   # host seconds: reset, feeds, epoch end, finish, sweeps
+
     def one_step(bufs, on_device):
         """bufs: per mate a device tensor, or {work index: (host pointer, nbytes)} for this rank's chunks."""
+        tl = [time.perf_counter()]
         eng.reset_pass1()
+        tl.append(time.perf_counter())
         for i in mine:
             mate, off, n, ob = work[i]
             if on_device:
                 eng.feed_text(bufs[mate].data_ptr() + off, n, on_device=True, fastq=True, ord_base=ob, ord_stride=2)
             else:
                 eng.feed_text(bufs[i][0], bufs[i][1], on_device=False, fastq=True, ord_base=ob, ord_stride=2)
+        tl.append(time.perf_counter())
         if xchg:
             xchg.end_epoch()
+        tl.append(time.perf_counter())
         st = eng.finish_pass1()
+        tl.append(time.perf_counter())
         hist, lin, rem = eng.sweeps()   # D2H of the histogram + counters: the step's result
+        tl.append(time.perf_counter())
+        if timeline is not None:
+            for j in range(5):
+                timeline[j] += tl[j + 1] - tl[j]
         return st, hist
 
     def timed(bufs, on_device, steps, warmup):
@@ -367,6 +378,12 @@ def main():
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
+        if timeline is not None and rank == 0:
+            n_all = steps + warmup
+            sys.stderr.write("[bench] host timeline, ms per step (warm-up included): reset %.2f, feeds %.2f, epoch end %.2f, finish_pass1 %.2f, sweeps %.2f\n"
+                             % tuple(1e3 * v / n_all for v in timeline))
+            for j in range(5):
+                timeline[j] = 0.0
         dev_ms = e0.elapsed_time(e1)
         ms = max(dev_ms, 0.0) if dev_ms > 0 else wall * 1e3
         if world > 1:
