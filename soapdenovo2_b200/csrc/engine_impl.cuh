@@ -55,7 +55,7 @@ struct ReadChunk {
 // C_RESERVED, C_DEFER, C_MAXU must stay consecutive (skm_flush resets them with one copy)
 // C_XERR .. C_MAXU must stay consecutive (an aggregation launch reports them with one copy); C_RESERVED, C_DEFER, C_MAXU are reset together
 enum Counter { C_DISTINCT = 0, C_INSTANCES, C_KEPT, C_LINEAR, C_REMOVED, C_MISC0, C_MISC1, C_MISC2, C_BADFMT, C_XERR, C_XUSED, C_RESERVED, C_DEFER, C_MAXU,
-               C_XSEGS, C_XEPOCH, C_COUNT = 16 };
+               C_XSEGS, C_XEPOCH, C_SPILLKEYS, C_COUNT = 17 };   // C_SPILLKEYS: keys the aggregation stored WITHOUT the fused sweeps
 
 template <int NW>
 class EngineT : public IEngine {
@@ -141,6 +141,14 @@ public:
     u64 xa_send_epoch_ = 0, xa_flushed_epoch_ = 0;
     u32 xa_seg_idx_ = 0;
     bool xa_flush_inflight_ = false;   // an aggregation launch whose outcome (deferred buckets, time) has not been read yet
+    // the end-of-pass sweeps fused into the aggregation flush: 0 = not done, 1 = done by this pass's only launch and still valid,
+    // 2 = done but the table has changed since (sweeps() runs k_sweep, which recomputes every flag it sets)
+    int inline_sweep_ = 0;
+    bool flush_sweeps_ = false;        // the launch in flight (and its deferred re-runs) applies the sweeps
+    DevBuf spill_list_;                // slots of the keys such a launch stored unswept (instances that did not fit a bucket's shared-memory table)
+    static constexpr u64 SPILL_CAP = 1ull << 22;
+    u64 pass_flushes_ = 0;             // aggregation launches since reset_pass1
+    bool pass_direct_ = false;         // per-instance inserts since reset_pass1
     u64* h_flush_ = nullptr;           // pinned: {C_RESERVED, C_DEFER, C_MAXU, C_XERR} as of the end of that launch
     cudaEvent_t ev_flush_ = nullptr;
     void skm_close_epoch(bool hard);
@@ -156,7 +164,7 @@ public:
     void skm_make_room(u64 n_rec, bool host_text);
     void skm_feed_chunk(size_t ci);
     void skm_fence();
-    void skm_flush();
+    void skm_flush(bool final_of_pass = false);
     void skm_reset();
     void skm_release();
 public:

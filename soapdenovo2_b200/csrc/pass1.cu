@@ -87,6 +87,8 @@ void EngineT<NW>::chop_insert_chunk(const ReadChunk& ch) {
     const int use_tma = smem <= 96 * 1024;
     if (use_tma && smem > 48 * 1024) cudaFuncSetAttribute(k_chop_insert<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_chop_insert<NW><<<blocks, INS_THREADS, use_tma ? smem : 0, st_>>>(tab_, kp_, ch.words, ch.len, ch.n_rec, W64_, ch.ord_base, ch.ord_stride, d_cnt_, use_tma);
+    pass_direct_ = true;
+    if (inline_sweep_ == 1) inline_sweep_ = 2;   // entries swept by an aggregation launch have changed since
     PG_CUDA(cudaGetLastError());
     p1_.launches += 1;
 }
@@ -198,12 +200,13 @@ void EngineT<NW>::finish_pass1(Pass1Stats* st) {
             throw std::runtime_error("pgb200: multi-GPU pass 1: call pgb200_xchg_fence, a barrier over all GPUs, then pgb200_flush before pgb200_finish_pass1");
     } else if (xa_buf_.p) {
         skm_close_epoch(false);
-        skm_flush();
+        skm_flush(true);   // nothing of this pass comes after it
     }
     settle_timing();
     sync();
     skm_flush_complete();
     read_counters();
+    if (inline_sweep_ == 1 && h_cnt_[C_SPILLKEYS] > SPILL_CAP) inline_sweep_ = 2;   // more unswept keys than the list holds
     check_format_counter();
     p1_.records = total_records_;
     p1_.reads_kept = h_cnt_[C_KEPT];
@@ -267,6 +270,9 @@ void EngineT<NW>::reset_pass1() {
     sync();
     chunks_.clear();
     skm_reset();
+    inline_sweep_ = 0;
+    pass_flushes_ = 0;
+    pass_direct_ = false;
     // keep the first arena block for the next pass, release the rest
     while (arena_.size() > 1) { cudaFree(arena_.back().first); arena_.pop_back(); }
     arena_used_ = 0;
@@ -293,21 +299,6 @@ void EngineT<NW>::reset_pass1() {
 // The table is streamed once: K <= 63 slots arrive with one 256-bit load each (key + payload in one 32 B sector), two slots per
 // thread in flight; the payload is written back only when a flag or a counter changed.
 template <int NW>
-__device__ __forceinline__ u64 sweep_payload(u64 p, int D, unsigned& rem, unsigned& lin, unsigned* s_hist) {
-    if (D > 0) {
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            unsigned l = pl_l(p, c), r = pl_r(p, c);
-            if (l > 0 && l <= (unsigned)D) p = pl_clear_l(p, c);
-            if (r > 0 && r <= (unsigned)D) p = pl_clear_r(p, c);
-        }
-        if ((p & PL_LLINKS_MASK) == 0 && (p & PL_RLINKS_MASK) == 0) { p |= PL_DELETED; rem++; }
-    }
-    atomicAdd(&s_hist[pl_cov(p)], 1u);
-    if (pl_nl(p) == 1 && pl_nr(p) == 1) { p |= PL_LINEAR; lin++; }
-    return p;
-}
-template <int NW>
 __global__ void __launch_bounds__(256) k_sweep(Table<NW> tab, int D, u64* hist, u64* counters) {
     __shared__ unsigned s_hist[256];
     __shared__ unsigned s_lin, s_rem;
@@ -331,13 +322,38 @@ __global__ void __launch_bounds__(256) k_sweep(Table<NW> tab, int D, u64* hist, 
             p0 = ldcg64(&s0->payload); p1 = ldcg64(&s1->payload);
         }
         if (!(k0a == EMPTY64 && k0b == EMPTY64)) {
-            const u64 q = sweep_payload<NW>(p0, D, rem, lin, s_hist);
+            const u64 q = sweep_payload(p0, D, rem, lin, s_hist);
             if (q != p0) s0->payload = q;
         }
         if (two && !(k1a == EMPTY64 && k1b == EMPTY64)) {
-            const u64 q = sweep_payload<NW>(p1, D, rem, lin, s_hist);
+            const u64 q = sweep_payload(p1, D, rem, lin, s_hist);
             if (q != p1) s1->payload = q;
         }
+    }
+    if (lin) atomicAdd(&s_lin, lin);
+    if (rem) atomicAdd(&s_rem, rem);
+    __syncthreads();
+    if (s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (u64)s_hist[threadIdx.x]);
+    if (threadIdx.x == 0) {
+        if (s_lin) atomicAdd(&counters[C_LINEAR], (u64)s_lin);
+        if (s_rem) atomicAdd(&counters[C_REMOVED], (u64)s_rem);
+    }
+}
+
+// the same for a list of slots (the keys an aggregation launch with fused sweeps stored unswept)
+template <int NW>
+__global__ void __launch_bounds__(256) k_sweep_list(Table<NW> tab, int D, const u64* __restrict__ list, u64 n, u64* hist, u64* counters) {
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned s_lin, s_rem;
+    s_hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { s_lin = 0; s_rem = 0; }
+    __syncthreads();
+    unsigned rem = 0, lin = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        Slot<NW>* s = tab.slots + list[i];
+        const u64 p = ldcg64(&s->payload);
+        const u64 q = sweep_payload(p, D, rem, lin, s_hist);
+        if (q != p) s->payload = q;
     }
     if (lin) atomicAdd(&s_lin, lin);
     if (rem) atomicAdd(&s_rem, rem);
@@ -355,11 +371,22 @@ void EngineT<NW>::sweeps(SweepStats* st) {
     create_table_if_needed();
     DevBuf& hist = hist_buf_;   // persistent: a cudaMalloc / cudaFree pair per call costs more than the sweep of a small table
     hist.ensure(256 * sizeof(u64));
-    PG_CUDA(cudaMemsetAsync(hist.p, 0, 256 * sizeof(u64), st_));
-    PG_CUDA(cudaMemsetAsync(d_cnt_ + C_LINEAR, 0, 2 * sizeof(u64), st_));
-    int D = (int)(signed char)prm_.D;   // deLowKmer is a `char` (inc/global.h:67)
-    k_sweep<NW><<<148 * 8, 256, 0, st_>>>(tab_, D, hist.template as<u64>(), d_cnt_);
-    PG_CUDA(cudaGetLastError());
+    // inline_sweep_ == 1: the pass was ONE aggregation launch into an empty table and nothing touched the table since -- its flush
+    // already applied the sweeps to every entry it stored (skm.cu), the histogram and the counters are complete
+    const int D = (int)(signed char)prm_.D;   // deLowKmer is a `char` (inc/global.h:67)
+    if (inline_sweep_ != 1) {
+        PG_CUDA(cudaMemsetAsync(hist.p, 0, 256 * sizeof(u64), st_));
+        PG_CUDA(cudaMemsetAsync(d_cnt_ + C_LINEAR, 0, 2 * sizeof(u64), st_));
+        k_sweep<NW><<<148 * 8, 256, 0, st_>>>(tab_, D, hist.template as<u64>(), d_cnt_);
+        PG_CUDA(cudaGetLastError());
+    } else if (h_cnt_[C_SPILLKEYS]) {
+        // the few keys whose instances went straight to the table (their bucket had more distinct k-mers than its shared-memory table)
+        const u64 n = h_cnt_[C_SPILLKEYS];
+        k_sweep_list<NW><<<(unsigned)std::min<u64>((n + 255) / 256, 148ull * 8), 256, 0, st_>>>(tab_, D, spill_list_.template as<u64>(), n, hist.template as<u64>(), d_cnt_);
+        PG_CUDA(cudaGetLastError());
+        PG_CUDA(cudaMemsetAsync(d_cnt_ + C_SPILLKEYS, 0, sizeof(u64), st_));   // a second call must not sweep (and count) them again
+        h_cnt_[C_SPILLKEYS] = 0;
+    }
     u64 h[256];
     PG_CUDA(cudaMemcpyAsync(h, hist.p, sizeof h, cudaMemcpyDeviceToHost, st_));
     read_counters();

@@ -346,6 +346,11 @@ struct SkmApplyArgs {
     u64* counters;            // C_RESERVED: keys the table is committed to hold; C_DEFER / C_MAXU: deferred buckets, their largest bound
     u64 limit;
     u32* deferred;
+    int sweep;                // 1: the flush applies the end-of-pass sweeps to every entry it stores (the launch is the whole pass)
+    int D;
+    u64* hist;                // [256] coverage histogram of the swept entries
+    u64* spill_list;          // slots of the keys stored unswept (spilled instances): the host sweeps them afterwards
+    u64 spill_cap;
 };
 constexpr u64 SKM_CREDIT = 1ull << 16;   // table room a CTA reserves at a time (keys)
 
@@ -366,6 +371,7 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS, SKM_APPLY_MIN_BLOCKS(NW)) k
     __shared__ u32 s_warp[WARPS];
     __shared__ u32 s_count, s_defer, s_batch;
     __shared__ unsigned s_new, s_tot_new, s_tot_spill;
+    __shared__ unsigned s_hist[256], s_lin, s_rem;   // the fused sweeps (a.sweep)
     SmemTable<NW, SKM_SLOTS, SKM_SOFT_LIMIT, unsigned short> st{s_dyn, s_dyn + NW * SKM_SLOTS, s_dyn + (NW + 1) * SKM_SLOTS, reinterpret_cast<unsigned short*>(s_dyn + (NW + 2) * SKM_SLOTS), &s_count};
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned lane_le = 0xffffffffu >> (31 - lane);
@@ -374,7 +380,10 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS, SKM_APPLY_MIN_BLOCKS(NW)) k
         st.pay[i] = PAYLOAD_FRESH;
         st.rnk[i] = ~0ull;
     }
-    if (tid == 0) { s_tot_new = 0; s_tot_spill = 0; }
+    if (tid == 0) { s_tot_new = 0; s_tot_spill = 0; s_lin = 0; s_rem = 0; }
+    static_assert(SKM_APPLY_THREADS == 256, "one histogram bin per thread");
+    s_hist[tid] = 0;
+    unsigned sw_lin = 0, sw_rem = 0;
     const int n_segs = (int)a.segs->n;
     const u32* my_so = tid < n_segs ? a.segs->segoff[tid] : nullptr;
     const u64* my_recs = tid < n_segs ? a.segs->recs[tid] : nullptr;
@@ -527,8 +536,14 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS, SKM_APPLY_MIN_BLOCKS(NW)) k
                     if (state == 1) st.apply(slot, in.left, in.right, rank);
                     else if (state == 3) {
                         // bucket holds more distinct k-mers than the shared-memory table: this instance goes to HBM directly (same result)
-                        my_new += table_insert(tab, in.canon, in.left, in.right, rank);
+                        u64 at;
+                        const bool fresh = table_insert(tab, in.canon, in.left, in.right, rank, &at);
+                        my_new += fresh;
                         tot_spill++;
+                        if (fresh && a.sweep) {   // its other instances follow the same way: swept after the launch, from this list
+                            const u64 n = atomicAdd((unsigned long long*)&a.counters[C_SPILLKEYS], 1ull);
+                            if (n < a.spill_cap) a.spill_list[n] = at;
+                        }
                     }
                 }
                 __syncwarp();
@@ -543,7 +558,11 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS, SKM_APPLY_MIN_BLOCKS(NW)) k
             Kmer<NW> k;
 #pragma unroll
             for (int w = 0; w < NW; w++) k.w[w] = st.key[w * SKM_SLOTS + idx];
-            my_new += table_merge(tab, k, st.pay[idx], st.rnk[idx]);
+            u64 agg = st.pay[idx];
+            if (a.sweep) agg = sweep_payload(agg, a.D, sw_rem, sw_lin, s_hist);   // this launch is the whole pass: the entry is final
+            const bool fresh = table_merge(tab, k, agg, st.rnk[idx]);
+            my_new += fresh;
+            if (a.sweep && !fresh) atomicAdd((unsigned long long*)&a.counters[C_SPILLKEYS], (unsigned long long)a.spill_cap + 1ull);   // (cannot happen in an empty table: makes the host run k_sweep)
             st.key[idx] = EMPTY64;
             st.pay[idx] = PAYLOAD_FRESH;
             st.rnk[idx] = ~0ull;
@@ -557,11 +576,16 @@ __global__ void __launch_bounds__(SKM_APPLY_THREADS, SKM_APPLY_MIN_BLOCKS(NW)) k
     if (tid == 0 && credit) atomicAdd((unsigned long long*)&a.counters[C_RESERVED], (unsigned long long)(0ull - credit));
     if (tot_new) atomicAdd(&s_tot_new, tot_new);
     if (tot_spill) atomicAdd(&s_tot_spill, tot_spill);
+    if (sw_lin) atomicAdd(&s_lin, sw_lin);
+    if (sw_rem) atomicAdd(&s_rem, sw_rem);
     __syncthreads();
     if (tid == 0) {
         if (s_tot_new) atomicAdd(&a.counters[C_DISTINCT], (u64)s_tot_new);
         if (s_tot_spill) atomicAdd(&a.counters[C_MISC2], (u64)s_tot_spill);
+        if (s_lin) atomicAdd(&a.counters[C_LINEAR], (u64)s_lin);
+        if (s_rem) atomicAdd(&a.counters[C_REMOVED], (u64)s_rem);
     }
+    if (a.sweep && s_hist[tid]) atomicAdd(&a.hist[tid], (u64)s_hist[tid]);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -855,6 +879,11 @@ void EngineT<NW>::skm_launch_apply(const u32* list, u32 n_list, u32* deferred_ou
     aa.segs = segs; aa.bucket_list = list; aa.n_list = n_list; aa.counters = d_cnt_;
     aa.limit = (u64)(0.85 * (double)cap_);
     aa.deferred = deferred_out;
+    aa.sweep = flush_sweeps_ ? 1 : 0;
+    aa.D = (int)(signed char)prm_.D;   // deLowKmer is a `char` (inc/global.h:67)
+    aa.hist = hist_buf_.template as<u64>();
+    aa.spill_list = spill_list_.template as<u64>();
+    aa.spill_cap = SPILL_CAP;
     int per_sm = 0, n_sm = 148;
     PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_skm_apply<NW>, SKM_APPLY_THREADS, skm_apply_smem<NW>()));
     PG_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, prm_.device));
@@ -869,11 +898,26 @@ void EngineT<NW>::skm_launch_apply(const u32* list, u32 n_list, u32* deferred_ou
 // Aggregate the closed epoch into the global table (several GPUs: only after every GPU has fenced -- the caller's barrier).
 // Returns as soon as the work is queued; skm_flush_complete (next epoch close, pgb200_finish_pass1) reads the outcome.
 template <int NW>
-void EngineT<NW>::skm_flush() {
+void EngineT<NW>::skm_flush(bool final_of_pass) {
     if (!xa_buf_.p || xa_flushed_epoch_ >= xa_send_epoch_) return;
     skm_flush_complete();
     if (xa_flushed_epoch_ + 1 != xa_send_epoch_) throw std::runtime_error("pgb200: internal: more than one unflushed exchange epoch");
     create_table_if_needed();
+    // The end-of-pass sweeps (K4) ride on this launch when it is the pass so far -- empty table, no launch and no per-instance insert
+    // before it: every entry it stores is then complete, and one pass over the table (5 ms per 2^29 slots) is saved.  Without -d the
+    // sweeps only SET flags that k_sweep recomputes anyway, so it is safe to do this speculatively: whatever touches the table later
+    // in the pass marks the result stale (inline_sweep_ = 2) and sweeps() runs k_sweep as before.  With -d the link counters are
+    // zeroed for good, so the launch must be known to be the last of the pass (finish_pass1 on one GPU).
+    flush_sweeps_ = pass_flushes_ == 0 && !pass_direct_ && inline_sweep_ == 0 && ((signed char)prm_.D <= 0 || final_of_pass);
+    if (flush_sweeps_) {
+        hist_buf_.ensure(256 * sizeof(u64));
+        spill_list_.ensure(SPILL_CAP * sizeof(u64));
+        PG_CUDA(cudaMemsetAsync(d_cnt_ + C_SPILLKEYS, 0, sizeof(u64), st_));
+        PG_CUDA(cudaMemsetAsync(hist_buf_.p, 0, 256 * sizeof(u64), st_));
+        PG_CUDA(cudaMemsetAsync(d_cnt_ + C_LINEAR, 0, 2 * sizeof(u64), st_));
+        inline_sweep_ = 1;
+    } else if (inline_sweep_ == 1) inline_sweep_ = 2;
+    pass_flushes_++;
     xa_flush_half_ = (int)(xa_flushed_epoch_ % xa_halves_);
     PG_CUDA(cudaEventRecord(ev_skm_[0], st_));
     const u32 n_owned = skm_own_hi_ - skm_own_lo_;
@@ -907,6 +951,7 @@ void EngineT<NW>::skm_flush_complete() {
         if (cap * sizeof(Slot<NW>) + (1ull << 28) > free_b)
             throw std::runtime_error("pgb200: k-mer table cannot grow further (out of HBM); use more GPUs");
         grow_table(cap);
+        if (inline_sweep_ == 1) inline_sweep_ = 2;   // the list of unswept keys holds slots of the table that was just replaced
         PG_CUDA(cudaEventRecord(ev_skm_[0], st_));
         skm_launch_apply(deferred[which], (u32)n_def, deferred[which ^ 1]);
         PG_CUDA(cudaEventRecord(ev_flush_, st_));
@@ -968,7 +1013,7 @@ void EngineT<NW>::skm_release() {
     template void EngineT<NW>::skm_flush_complete();                         \
     template void EngineT<NW>::skm_launch_apply(const u32*, u32, u32*);      \
     template u64 EngineT<NW>::skm_room_estimate(u64);                        \
-    template void EngineT<NW>::skm_flush();                                  \
+    template void EngineT<NW>::skm_flush(bool);                              \
     template void EngineT<NW>::skm_reset();                                  \
     template void EngineT<NW>::skm_release();
 PGB_INST(2)

@@ -62,6 +62,27 @@ PG_HD u64 payload_apply(u64 p, unsigned left, unsigned right) {
     return (p + inc) & ~PL_SINGLE;
 }
 
+// The per-entry sweeps of pass 1's end (K4): delow (thread_delow: zero every link counter <= D, deleted = 1 if nothing is left), mark
+// (thread_mark: linear = 1 iff exactly one non-zero left and one non-zero right link, NO deleted check there), histogram of cov.
+// Used by k_sweep (pass1.cu) and, fused, by the aggregation kernel's flush (skm.cu).  The linear flag is recomputed, not inherited.
+#if defined(__CUDACC__)
+__device__ __forceinline__ u64 sweep_payload(u64 p, int D, unsigned& rem, unsigned& lin, unsigned* s_hist) {
+    p &= ~PL_LINEAR;
+    if (D > 0) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            unsigned l = pl_l(p, c), r = pl_r(p, c);
+            if (l > 0 && l <= (unsigned)D) p = pl_clear_l(p, c);
+            if (r > 0 && r <= (unsigned)D) p = pl_clear_r(p, c);
+        }
+        if ((p & PL_LLINKS_MASK) == 0 && (p & PL_RLINKS_MASK) == 0) { p |= PL_DELETED; rem++; }
+    }
+    atomicAdd(&s_hist[pl_cov(p)], 1u);
+    if (pl_nl(p) == 1 && pl_nr(p) == 1) { p |= PL_LINEAR; lin++; }
+    return p;
+}
+#endif
+
 template <int NW>
 struct Slot;
 template <>
@@ -205,9 +226,10 @@ PG_D void slot_apply(Slot<NW>* s, u64 cur_payload, u64 cur_rank, unsigned left, 
 
 // Fused find-or-claim + apply for one k-mer instance.  Returns true if this call inserted the key.
 template <int NW>
-PG_D bool table_insert(const Table<NW>& t, const Kmer<NW>& k, unsigned left, unsigned right, u64 rank) {
+PG_D bool table_insert(const Table<NW>& t, const Kmer<NW>& k, unsigned left, unsigned right, u64 rank, u64* idx_out = nullptr) {
     bool claimed;
     u64 idx = table_find_or_claim(t, k, &claimed);
+    if (idx_out) *idx_out = idx;
     Slot<NW>* s = t.slots + idx;
     U128 cur = claimed ? U128{PAYLOAD_FRESH, EMPTY64} : ldcg128(&s->payload);
     slot_apply(s, cur.a, cur.b, left, right, rank);
@@ -216,7 +238,7 @@ PG_D bool table_insert(const Table<NW>& t, const Kmer<NW>& k, unsigned left, uns
 // K <= 63: the whole 32 B slot arrives with ONE 256-bit load per probe, so a hit needs no second read before the CAS and
 // a fresh claim knows the {payload, rank} it will find (the memset state).
 template <>
-PG_D bool table_insert<2>(const Table<2>& t, const Kmer<2>& k, unsigned left, unsigned right, u64 rank) {
+PG_D bool table_insert<2>(const Table<2>& t, const Kmer<2>& k, unsigned left, unsigned right, u64 rank, u64* idx_out) {
     u64 idx = table_hash(k) & t.mask;
     bool claimed = false;
     U128 cur;
@@ -233,6 +255,7 @@ PG_D bool table_insert<2>(const Table<2>& t, const Kmer<2>& k, unsigned left, un
         }
         idx = (idx + 1) & t.mask;
     }
+    if (idx_out) *idx_out = idx;
     slot_apply(s, cur.a, cur.b, left, right, rank);
     return claimed;
 }

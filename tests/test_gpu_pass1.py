@@ -146,3 +146,31 @@ def test_aggregated_stress_paths(tmp_path, monkeypatch, K, flav, buckets, arena_
     eng.build_layout()
     assert eng.dump_nodes() == open(dump, "rb").read()
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,flav,D,buckets", [(31, 0, 0, "2"), (63, 0, 1, "3"), (91, 1, 0, "2"), (31, 0, 2, "0")])
+def test_fused_sweeps_with_spilled_keys(tmp_path, monkeypatch, K, flav, D, buckets):
+    """One aggregation launch into a table that is large enough (no growth): the end-of-pass sweeps ride on its flush, and the keys
+    whose instances went straight to the table (2-3 buckets: almost every k-mer spills past the shared-memory table) are swept from
+    the launch's list afterwards.  kmerFreq, the linear / deleted flags (table dump) and the counters equal the oracle's; a second
+    sweeps() call returns the same numbers."""
+    if os.environ.get("PGB200_SKM") == "0":
+        pytest.skip("aggregated path only")
+    monkeypatch.setenv("PGB200_SKM", "1")
+    if buckets != "0":
+        monkeypatch.setenv("PGB200_SKM_BUCKETS", buckets)
+    cfg = synth.scenario_pe_fastq(str(tmp_path))
+    mod, dump = str(tmp_path / "mod"), str(tmp_path / "mod.table")
+    extra = ("-1", "-T", dump, "-a", "1") + (("-d", str(D)) if D else ())
+    util.run_model(util.MODEL127 if flav else util.MODEL63, cfg, mod, K, 4, extra)
+    eng = api.PregraphEngine(K=K, P=4, initG=1, D=D, flavour127=flav, max_rd_len=150)
+    for mate, fn in enumerate(("pe_1.fq", "pe_2.fq")):
+        eng.feed_text(open(tmp_path / fn, "rb").read(), fastq=True, ord_base=mate, ord_stride=2)
+    eng.finish_pass1()
+    hist, lin, rem = eng.sweeps()
+    assert api.kmerfreq_text(hist) == open(mod + ".kmerFreq", "rb").read()
+    assert (hist, lin, rem) == eng.sweeps()
+    eng.build_layout()
+    assert eng.dump_nodes() == open(dump, "rb").read()
+    eng.close()
