@@ -49,7 +49,11 @@ __global__ void __launch_bounds__(256) k_nl_count(const uint4* __restrict__ text
 #pragma unroll
         for (int it = 0; it < NL_ITERS; it++) {
             const u64 grp = tile * NL_GROUPS + it * 32 + lane;
-            if (grp < n_groups) cnt += __popc(nl_mask16(text, nbytes, grp));
+            if ((grp + 1) * 16 <= nbytes) {   // a whole group: every equal byte is 0xFF in the compare result, 8 set bits
+                const uint4 v = __ldg(text + grp);
+                cnt += (__popc(__vcmpeq4(v.x, 0x0A0A0A0Au)) + __popc(__vcmpeq4(v.y, 0x0A0A0A0Au)) + __popc(__vcmpeq4(v.z, 0x0A0A0A0Au)) +
+                        __popc(__vcmpeq4(v.w, 0x0A0A0A0Au))) >> 3;
+            } else if (grp < n_groups) cnt += __popc(nl_mask16(text, nbytes, grp));
         }
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         if (lane == 0) tile_cnt[tile] = cnt;
