@@ -11,7 +11,10 @@
 //                                     for the others.  Partition and "all-to-all" are the same kernel; no library collective, no
 //                                     staging buffer, no second pass over the records.
 //   flush (end of pass 1 / arena full):  k_skm_apply over the owned buckets; buckets whose worst case does not fit the global table
-//                                     are deferred, the table grows, the deferred buckets run again.
+//                                     are deferred, the table grows, the deferred buckets run again.  When the launch is the whole
+//                                     pass (the normal case) the end-of-pass sweeps -- delow, linear flag, coverage histogram
+//                                     (thread_delow / thread_mark / freqStat, prlHashReads.c:953-1132) -- are applied to every
+//                                     entry as it is stored: no separate pass over the table.
 // Replaces, for the same result, chopKmer4read + the owner filter + put_kmerset (prlHashReads.c:163-259, 79-90; newhash.c:473-528).
 #include "engine_impl.cuh"
 #include "skm.cuh"

@@ -58,6 +58,9 @@ def test_contig_reads_the_sidecar(tmp_path, flav, K, extra):
     # and the way back: the sidecar regenerates the reference's .edge.gz byte for byte (text AND deflate stream)
     api.sidecar_to_edge_gz(side_run)
     util.compare(ref, side_run, ["edge.gz"])
+    os.remove(side_run + ".edge.gz")
+    util.run([api.BIN127 if flav else api.BIN63, "edgegz", "-g", side_run])   # the same through the CLI
+    util.compare(ref, side_run, ["edge.gz"])
 
 
 def test_sidecar_converter_rejects_garbage(tmp_path):
