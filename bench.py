@@ -313,7 +313,9 @@ def main():
         else:
             per_rank = max(1, round(10 / world))                   # chunks per mate and rank: 10 x 1 M reads at N=1
             chunk_reads = -(-n_pairs // (world * per_rank))
-    est_distinct = int(total_genome * (2.3 if K <= 63 else 3.6)) + 1_000_000   # ~K error k-mers per substitution
+    # genome + the k-mers the substitutions create: 0.001 x coverage errors per genome base, each covered by ~36 (K=63) / ~19 (K=127:
+    # only 24 k-mers per 150 bp read) k-mers of its read -- measured at 30x: 2.07 x and 1.56 x the genome size; 10 % head room
+    est_distinct = int(total_genome * 1.1 * (1.0 + 0.001 * args.coverage * (36 if K <= 63 else 19))) + 1_000_000
     slots = 1 << max(20, (int(est_distinct / world * 2.2 * float(os.environ.get('PGB200_BENCH_SLOTS_MULT', '1')))).bit_length())
     eng = api.PregraphEngine(K=K, P=8, initG=0, flavour127=int(K > 63), max_rd_len=RD_LEN, device=local_rank, table_slots=slots, world=world, rank=rank,
                              verbose=int(os.environ.get("PGB200_VERBOSE", "0")))
