@@ -319,15 +319,24 @@ def main():
     slots = 1 << max(20, (int(est_distinct / world * 2.2 * float(os.environ.get('PGB200_BENCH_SLOTS_MULT', '1')))).bit_length())
     eng = api.PregraphEngine(K=K, P=8, initG=0, flavour127=int(K > 63), max_rd_len=RD_LEN, device=local_rank, table_slots=slots, world=world, rank=rank,
                              verbose=int(os.environ.get("PGB200_VERBOSE", "0")))
-    chunk = chunk_reads * REC_BYTES
-    work = []   # (mate, byte offset, nbytes, ordinal base)
-    for mate, t in enumerate((t1, t2)):
-        off = 0
-        while off < t.numel():
-            n = min(chunk, t.numel() - off)
-            work.append((mate, off, n, (pair_base + off // REC_BYTES) * 2 + mate))
-            off += n
+    def make_work(reads_per_chunk):
+        out = []   # (mate, byte offset, nbytes, ordinal base)
+        for mate, t in enumerate((t1, t2)):
+            off = 0
+            while off < t.numel():
+                n = min(reads_per_chunk * REC_BYTES, t.numel() - off)
+                out.append((mate, off, n, (pair_base + off // REC_BYTES) * 2 + mate))
+                off += n
+        return out
+
+    work = make_work(chunk_reads)
     mine = list(range(len(work))) if weak else pdist.deal(len(work), world, rank)
+    # One GPU, text already in HBM: nothing has to overlap with a copy, so the feed uses fewer, larger chunks (4 M reads = 0.63 GB of
+    # text per feed_text call; every kernel of the front end then runs 6 times per step instead of 20: 64.8 vs 67.5 ms per step on the
+    # same box).  The host-buffer pass (e2e) keeps 1 M-read chunks: there the chunk is the unit of the copy / compute overlap.
+    chunk_reads_dev = 4_000_000 if (world == 1 and not weak and not args.chunk_reads) else chunk_reads
+    work_dev = make_work(chunk_reads_dev) if chunk_reads_dev != chunk_reads else work
+    mine_dev = list(range(len(work_dev))) if work_dev is not work else mine
     total_instances = 2 * n_pairs * (world if weak else 1) * (RD_LEN - K + 1)
     xchg = None
     if world > 1:
@@ -343,8 +352,8 @@ def main():
         tl = [time.perf_counter()]
         eng.reset_pass1()
         tl.append(time.perf_counter())
-        for i in mine:
-            mate, off, n, ob = work[i]
+        for i in (mine_dev if on_device else mine):
+            mate, off, n, ob = (work_dev if on_device else work)[i]
             if on_device:
                 eng.feed_text(bufs[mate].data_ptr() + off, n, on_device=True, fastq=True, ord_base=ob, ord_stride=2)
             else:
@@ -498,7 +507,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
         "config": {"workload": workload, "reads": 2 * n_pairs_total, "kmer_instances": r["instances"], "distinct_kmers": r["distinct"],
-                   "instances_per_s": r["instances"] / (r["ms"] / 1e3), "table_slots_per_gpu": int(st.table_slots), "chunk_reads": chunk_reads, "chunks": len(work),
+                   "instances_per_s": r["instances"] / (r["ms"] / 1e3), "table_slots_per_gpu": int(st.table_slots), "chunk_reads": chunk_reads_dev, "chunks": len(work_dev), "e2e_chunk_reads": chunk_reads,
                    "parallelism": (f"minimizer buckets owned in {world} contiguous ranges; chunk i decoded + partitioned by rank i % {world}; super-k-mer records stored straight into the "
                                    f"owner GPU's arena by the partition kernel (NVLink peer stores over CUDA IPC mappings, no library collective on the data path); one barrier per step"
                                    if world > 1 else "1 GPU"),
