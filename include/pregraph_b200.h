@@ -106,7 +106,10 @@ int pgb200_xchg_room(pgb200_engine *e, uint64_t n_rec);
 int pgb200_absorb(pgb200_engine *e, pgb200_engine *other);
 int pgb200_finish_pass1(pgb200_engine *e, pgb200_pass1_stats *st);
 int pgb200_reset_pass1(pgb200_engine *e);
-/* delow (-d) + mark linear + coverage histogram: hist[c] = number of k-mers with coverage c (the .kmerFreq lines are hist[1..255]) */
+/* delow (-d) + mark linear + coverage histogram (thread_delow / thread_mark / freqStat, prlHashReads.c:953-1132): hist[c] = number of
+ * k-mers with coverage c (the .kmerFreq lines are hist[1..255]).  When the pass was one aggregation launch the sweeps were already
+ * applied to every entry as it was stored and this call only returns the numbers; otherwise it runs the pass over the table.  May be
+ * called again: same numbers.                                                                                                      */
 int pgb200_sweeps(pgb200_engine *e, long long hist[256], uint64_t *linear_marked, uint64_t *removed);
 
 int pgb200_build_layout(pgb200_engine *e);
