@@ -129,6 +129,11 @@ int pgb200_output_vertex(pgb200_engine *e, const char *outfile_prefix, pgb200_gr
 /* Host logic only (no GPU): the read-stream plan of a library config -- one "mate fastq reverse_seq cut path" line per file in
  * the order the reference opens them (scan_libInfo lib.c:130-506, nextValidIndex readseq1by1.c:595-674); first line "max_rd_len N". */
 int pgb200_plan_files(const char *cfg, char *out, size_t cap);
+/* Host logic only: where the stage cuts a text buffer that ends in the middle of a record -- the offset of the last record start such
+ * that buf[0..off) holds whole records and the record at `off` is known to be a record start (FASTA: a line starting with '>';
+ * FASTQ: a line starting with '@' whose line after next starts with '+', which a quality line starting with '@' never has).
+ * 0: no such position in the buffer (the caller reads more).  The reference reads line by line (readseq1by1.c:138-209, 279-360). */
+size_t pgb200_cut_chunk(const char *buf, size_t n, int fastq);
 
 /* f2: binary edge sidecar `<prefix>.edge.b200` for a `contig` that links csrc/contig_sidecar.c -- the edges without
  * the gzip'ed text (the reference's loader: loadPreGraph.c:448-544).  Written by the stage when PGB200_EDGE_SIDECAR is set (the

@@ -22,7 +22,7 @@ EXPORTS = [
     "pgb200_xchg_setup", "pgb200_xchg_export", "pgb200_xchg_import", "pgb200_xchg_base", "pgb200_xchg_import_ptr", "pgb200_xchg_fence", "pgb200_flush", "pgb200_xchg_room", "pgb200_absorb",
     "pgb200_finish_pass1", "pgb200_reset_pass1", "pgb200_sweeps",
     "pgb200_build_layout", "pgb200_node_count", "pgb200_dump_nodes", "pgb200_remove_tips", "pgb200_kmer2edges",
-    "pgb200_read2edge", "pgb200_output_vertex", "pgb200_edge_text_to_sidecar", "pgb200_sidecar_to_edge_gz", "pgb200_plan_files", "pgb200_pregraph_main", "call_pregraph",
+    "pgb200_read2edge", "pgb200_output_vertex", "pgb200_edge_text_to_sidecar", "pgb200_sidecar_to_edge_gz", "pgb200_plan_files", "pgb200_cut_chunk", "pgb200_pregraph_main", "call_pregraph",
 ]
 
 
@@ -87,6 +87,8 @@ def load():
     lib.pgb200_edge_text_to_sidecar.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_uint64, C.c_char_p]
     lib.pgb200_sidecar_to_edge_gz.argtypes = [C.c_char_p]
     lib.pgb200_plan_files.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+    lib.pgb200_cut_chunk.restype = C.c_size_t
+    lib.pgb200_cut_chunk.argtypes = [C.c_char_p, C.c_size_t, C.c_int]
     lib.pgb200_pregraph_main.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int]
     _lib = lib
     return lib
@@ -215,6 +217,11 @@ def plan_files(cfg: str):
         m, fq, rev, cut, path = l.split(" ", 4)
         plan.append((int(m), int(fq), int(rev), int(cut), path))
     return int(lines[0].split()[1]), plan
+
+
+def cut_chunk(buf: bytes, fastq: bool) -> int:
+    """Host logic only: offset at which the stage would cut this text buffer (0: it would read more first)."""
+    return int(load().pgb200_cut_chunk(buf, len(buf), int(fastq)))
 
 
 def kmerfreq_text(hist) -> bytes:

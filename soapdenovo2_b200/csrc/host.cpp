@@ -462,6 +462,9 @@ static size_t last_record_start(const char* buf, size_t n, bool fastq) {
     }
 }
 
+// CPU-testable view of the chunk cutter (host logic only)
+extern "C" size_t pgb200_cut_chunk(const char* buf, size_t n, int fastq) { return last_record_start(buf, n, fastq != 0); }
+
 static double now_s() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
 
 // One pinned staging buffer; chunk i goes to engine i % G.  pgb200_feed_text returns when the chunk's H2D copy is done, its kernels

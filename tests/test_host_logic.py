@@ -55,3 +55,48 @@ def test_config_quirks(tmp_path):
     assert mrl == 100
     assert [os.path.basename(p[4]) for p in plan] == ["z1.fq", "z2.fq", "x.fa", "y.fq"]
     assert [p[4] for p in plan] == _ref_order(cfg, os.path.join(d, "ref"))
+
+
+def _fq(n, qual=None, eol=b"\n"):
+    out = b""
+    for i in range(n):
+        q = qual(i) if qual else b"I" * 8
+        out += b"@r%d" % i + eol + b"ACGTACGT" + eol + b"+" + eol + q + eol
+    return out
+
+
+def test_chunk_cut_keeps_whole_records():
+    """The feeder cuts a buffer that ends inside a record at the last position that is KNOWN to start a record."""
+    whole = _fq(5)
+    rec = len(whole) // 5
+    # the buffer ends inside record 4 (header + part of the sequence line): everything before record 3's start is certainly whole
+    # (record 3 itself is the last one whose '+' line is visible), so the cut is at record 3
+    assert api.cut_chunk(whole[: 4 * rec + 9], True) == 3 * rec
+    # it ends exactly at a record boundary: the last record start found is still the cut (the tail record goes with the next read)
+    assert api.cut_chunk(whole, True) == 4 * rec
+    # a single, incomplete record: nothing to cut yet
+    assert api.cut_chunk(whole[: rec - 3], True) == 0
+    assert api.cut_chunk(b"", True) == 0
+
+
+def test_chunk_cut_is_not_fooled_by_quality_lines_starting_with_at():
+    """'@' is a valid quality character (Phred 31): a quality line may start with it.  Two lines after a real header comes the '+'
+    line; two lines after such a quality line comes a sequence line."""
+    whole = _fq(6, qual=lambda i: b"@" + b"I" * 7)
+    rec = len(whole) // 6
+    for cut_at in (5 * rec + 2, 5 * rec + 12, 5 * rec + rec - 1):
+        off = api.cut_chunk(whole[:cut_at], True)
+        assert off % rec == 0 and 0 < off <= 4 * rec + rec, (cut_at, off)
+        assert whole[off:off + 2] == b"@r"
+    # the same with CRLF line ends
+    crlf = _fq(6, qual=lambda i: b"@" + b"I" * 7, eol=b"\r\n")
+    rec = len(crlf) // 6
+    off = api.cut_chunk(crlf[: 5 * rec + 7], True)
+    assert off % rec == 0 and off > 0 and crlf[off:off + 2] == b"@r"
+
+
+def test_chunk_cut_fasta():
+    fa = b"".join(b">s%d\nACGTACGTAC\n" % i for i in range(4))
+    rec = len(fa) // 4
+    assert api.cut_chunk(fa[: 3 * rec + 4], False) == 3 * rec      # '>' starts a record, the rest of it follows with the next read
+    assert api.cut_chunk(fa[: rec - 2], False) == 0
