@@ -50,6 +50,23 @@ def test_pe_fastq_127mer_build(pe_cfg, tmp_path, K, P, extra):
     util.compare(ref, mod, util.SUFFIXES_R if "-R" in extra else util.SUFFIXES)
 
 
+@pytest.mark.parametrize("K,P,extra", [(63, 8, ("-d", "2", "-R")), (45, 5, ("-d", "1", "-a", "1", "-R")), (23, 2, ())])
+def test_pe_fastq_more_k_and_cutoffs(pe_cfg, tmp_path, K, P, extra):
+    """-d together with -R at K = 63 (delow before the edges and the read paths), an odd K between the word sizes, the default K."""
+    ref, mod = str(tmp_path / "ref"), str(tmp_path / "mod")
+    util.run_ref(util.REF63, pe_cfg, ref, K, P, extra)
+    util.run_model(util.MODEL63, pe_cfg, mod, K, P, extra)
+    util.compare(ref, mod, util.SUFFIXES_R if "-R" in extra else util.SUFFIXES)
+
+
+def test_multilib_127mer_build(tmp_path):
+    cfg = synth.scenario_multilib(str(tmp_path))
+    ref, mod = str(tmp_path / "ref"), str(tmp_path / "mod")
+    util.run_ref(util.REF127, cfg, ref, 99, 4, ("-R", "-d", "1"))
+    util.run_model(util.MODEL127, cfg, mod, 99, 4, ("-R", "-d", "1"))
+    util.compare(ref, mod, util.SUFFIXES_R)
+
+
 def test_multilib_k63(tmp_path):
     cfg = synth.scenario_multilib(str(tmp_path))
     ref, mod = str(tmp_path / "ref"), str(tmp_path / "mod")
