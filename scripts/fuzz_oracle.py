@@ -40,6 +40,7 @@ def one_case(seed: int):
         elif kind == 2:
             cfg = synth.scenario_multilib(d, genome_len=int(rng.integers(10000, 50000)), seed=seed)
         else:
+            K = min(K, 99)   # its reads are at most 100 bases long (the reference itself fails on a library without a single k-mer)
             cfg = synth.scenario_adversarial(d, seed=seed, crlf=bool(rng.integers(0, 2)), K_hint=min(K, 97))
         ref_bin, mod_bin = (util.REF127, util.MODEL127) if big else (util.REF63, util.MODEL63)
         ref, mod = os.path.join(d, "ref"), os.path.join(d, "mod")
