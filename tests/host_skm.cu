@@ -191,7 +191,8 @@ static int owner_case(u32 B, int world) {
     return errors;
 }
 
-int main() {
+int main(int argc, char** argv) {
+    if (argc > 1) rng_state ^= strtoull(argv[1], nullptr, 0) * 0x9E3779B97F4A7C15ull;   // other random reads (fuzzing); default: the fixed set
     int e = 0;
     {
         int oe = 0;
